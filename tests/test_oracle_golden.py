@@ -1,0 +1,160 @@
+"""Pin the CPU oracle (oracle/*.py) against fixtures produced by the reference's
+own modules (tests/golden/make_golden.py).  CPU-only; no GPU, no /root/reference."""
+import numpy as np
+import torch
+
+from audiogpt_b200 import specs
+from oracle import diffusion_ref as dr
+from oracle import hifigan_ref as hr
+from oracle import ldm_ref as lr
+from conftest import load_golden, rel_rmse
+
+T = torch.tensor
+
+
+def test_hifigan_small():
+    g = load_golden("hifigan_small")
+    h = specs.HIFIGAN_SMALL
+    sd = specs.synth_hifigan(h, 1234)
+    wav = hr.hifigan_forward(sd, h, T(g["mel"]))
+    assert wav.shape == (2, 1, 24 * 256)
+    assert rel_rmse(wav, g["wav"]) < 1e-6   # same torch ops; summation order may differ per box
+
+
+def test_hifigan_weight_norm_fold():
+    g = load_golden("hifigan_small")
+    h = specs.HIFIGAN_SMALL
+    sd = specs.synth_hifigan(h, 1234)
+    sd_wn = {}
+    for k, v in sd.items():
+        if k.endswith(".weight"):
+            sd_wn[k[:-6] + "weight_g"] = T(g["wn::" + k[:-6] + "weight_g"])
+            sd_wn[k[:-6] + "weight_v"] = v * 3.0
+        else:
+            sd_wn[k] = v
+    assert sorted(sd_wn.keys()) == list(g["wn_keys"])
+    wav = hr.hifigan_forward(sd_wn, h, T(g["mel"]))
+    # folding g*v/||v|| on our side vs torch's weight-norm hook: same formula, fp32 rounding may differ
+    assert rel_rmse(wav, g["wav_wn"]) < 1e-6
+
+
+def test_hifigan_resblock2():
+    g = load_golden("hifigan_small_rb2")
+    h = dict(specs.HIFIGAN_SMALL, resblock="2", resblock_dilation_sizes=[[1, 3], [1, 3], [1, 3]])
+    wav = hr.hifigan_forward(specs.synth_hifigan(h, 4321), h, T(g["mel"]))
+    assert rel_rmse(wav, g["wav"]) < 1e-6   # same torch ops; summation order may differ per box
+
+
+def test_hifigan_nsf():
+    g = load_golden("hifigan_small_nsf")
+    h = dict(specs.HIFIGAN_SMALL, use_pitch_embed=True, audio_sample_rate=24000)
+    wav = hr.hifigan_forward(specs.synth_hifigan(h, 5678), h, T(g["mel"]), T(g["har_source"]))
+    assert rel_rmse(wav, g["wav"]) < 1e-6   # same torch ops; summation order may differ per box
+
+
+def test_hifigan_v1_c1():
+    g = load_golden("hifigan_v1_c1")
+    h = specs.HIFIGAN_V1
+    mel = specs.synth_tensor((1, 80, 400), seed=0, scale=2.0, shift=-4.0)
+    wav = hr.hifigan_forward(specs.synth_hifigan(h, 1234), h, mel)
+    assert wav.shape == (1, 1, 102400)
+    # thread-count dependent summation order inside torch's conv => not bit-exact across boxes
+    assert rel_rmse(wav[0, 0, :4096], g["wav_head"]) < 2e-5
+    assert rel_rmse(wav[0, 0, ::37], g["wav_stride"]) < 2e-5
+    assert abs(hr.hifigan_flops(h, 400) / 245.64e9 - 1) < 0.01
+
+
+def test_schedule_tables_bit_exact():
+    g = load_golden("diffusion_small")
+    tab = dr.schedule_tables(dr.linear_betas(100, 0.06))
+    for k, v in tab.items():
+        assert torch.equal(v, T(g["tab::" + k])), k
+    tab1000 = dr.schedule_tables(dr.linear_betas(1000, 0.02))
+    assert torch.equal(tab1000["alphas_cumprod"], T(g["tab1000::alphas_cumprod"]))
+
+
+def test_diffnet_and_p_sample():
+    g = load_golden("diffusion_small")
+    cfg = specs.DIFFNET_SMALL
+    sd = specs.synth_diffnet(cfg, 2024)
+    x, cond, t = T(g["x"]), T(g["cond"]), T(g["t"])
+    eps = dr.diffnet_forward(sd, cfg, x, t, cond)
+    assert rel_rmse(eps, g["eps"]) < 1e-6
+    tab = dr.schedule_tables(dr.linear_betas(100, 0.06))
+    bank = specs.synth_tensor((100,) + tuple(x.shape), seed=23)
+    fn = lambda a, b, c: dr.diffnet_forward(sd, cfg, a, b, c)
+    xx = x
+    for n, i in enumerate(g["steps"]):
+        xx = dr.p_sample(tab, fn, xx, torch.full((x.shape[0],), int(i), dtype=torch.long), cond, bank[int(i)])
+        assert rel_rmse(xx, g["xs"][n + 1]) < 1e-5, i
+    xl = dr.sample_loop(sd, cfg, tab, x, cond, bank)
+    assert rel_rmse(xl, g["x_loop"]) < 1e-4
+    smin, smax = T(specs.SPEC_MIN)[None, None], T(specs.SPEC_MAX)[None, None]
+    mel = dr.denorm_spec(xl[:, 0].transpose(1, 2), smin, smax)
+    assert rel_rmse(mel, g["mel_out"]) < 1e-4
+    xq = dr.q_sample(tab, dr.norm_spec(T(g["fs2_mel"]), smin, smax).transpose(1, 2)[:, None],
+                     torch.tensor([70]), T(g["q_noise"]))
+    assert rel_rmse(xq, g["x_q"]) < 1e-6
+
+
+def test_plms():
+    g = load_golden("diffusion_small")
+    cfg = specs.DIFFNET_SMALL
+    sd = specs.synth_diffnet(cfg, 2024)
+    tab = dr.schedule_tables(dr.linear_betas(1000, 0.02))
+    fn = lambda a, b, c: dr.diffnet_forward(sd, cfg, a, b, c)
+    x, cond = T(g["x"])[:1], T(g["cond"])[:1]
+    hist, snaps = [], []
+    for i in reversed(range(0, 1000, 10)):
+        x = dr.p_sample_plms(tab, fn, x, torch.full((1,), i, dtype=torch.long), 10, cond, hist)
+        if i in (990, 980, 970, 960, 500, 0):
+            snaps.append(x)
+    for n, s in enumerate(snaps):
+        assert rel_rmse(s, g["plms"][n]) < 1e-4, n
+    assert rel_rmse(x, g["plms_final"]) < 1e-4
+
+
+def test_diffnet_base_forward():
+    g = load_golden("diffusion_base_fwd")
+    cfg = specs.DIFFNET_BASE
+    sd = specs.synth_diffnet(cfg, 2025)
+    xb = specs.synth_tensor((2, 1, 80, 100), seed=31)
+    cb = specs.synth_tensor((2, 256, 100), seed=32)
+    eb = dr.diffnet_forward(sd, cfg, xb, torch.tensor([99, 3]), cb)
+    assert rel_rmse(eb, g["eps"]) < 1e-5
+    assert abs(dr.diffnet_flops_per_frame(cfg) / 26.44e6 - 1) < 0.01
+
+
+def test_unet_small_and_ddim():
+    g = load_golden("ldm_small")
+    cfg = specs.UNET_SMALL
+    sd = specs.synth_unet(cfg, 3030)
+    eps = lr.unet_forward(sd, cfg, T(g["x"]), T(g["t"]), T(g["ctx"]))
+    assert rel_rmse(eps, g["eps"]) < 1e-5
+    sch = lr.ldm_schedule()
+    assert torch.equal(sch["alphas_cumprod"], T(g["alphas_cumprod"]))
+    tab = lr.ddim_tables(sch["alphas_cumprod"], 10)
+    assert np.array_equal(tab["timesteps"], g["ddim_timesteps"])
+    assert torch.equal(torch.as_tensor(tab["alphas"]), T(g["ddim_alphas"]))
+    assert np.array_equal(np.asarray(tab["alphas_prev"], dtype=np.float64), g["ddim_alphas_prev"])
+    assert torch.equal(torch.as_tensor(tab["sqrt_one_minus_alphas"]), T(g["ddim_sqrt_one_minus_alphas"]))
+    fn = lambda x, t, c: lr.unet_forward(sd, cfg, x, t, c)
+    out = lr.ddim_sample(fn, sch["alphas_cumprod"], 10, T(g["x_T"]), T(g["ctx"]), T(g["uc"]), 1.5)
+    assert rel_rmse(out, g["ddim10"]) < 1e-4
+    out5 = lr.ddim_sample(fn, sch["alphas_cumprod"], 5, T(g["x_T"]), T(g["ctx"]))
+    assert rel_rmse(out5, g["ddim5_nocfg"]) < 1e-4
+
+
+def test_unet_txt2audio_forward():
+    g = load_golden("ldm_txt2audio")
+    cfg = specs.UNET_TXT2AUDIO
+    sd = specs.synth_unet(cfg, 4040)
+    xf = torch.tensor(np.random.RandomState(55).randn(1, 4, 10, 78), dtype=torch.float32)
+    cf = specs.synth_tensor((1, 77, 1024), seed=5)
+    ucf = specs.synth_tensor((1, 77, 1024), seed=6)
+    ef = lr.unet_forward(sd, cfg, torch.cat([xf, xf]), torch.tensor([991, 991]), torch.cat([ucf, cf]))
+    assert rel_rmse(ef, g["eps_pair"]) < 2e-5
+    sch = lr.ldm_schedule()
+    fn = lambda x, t, c: lr.unet_forward(sd, cfg, x, t, c)
+    out = lr.ddim_sample(fn, sch["alphas_cumprod"], 100, xf, cf, ucf, 1.5, steps_limit=4)
+    assert rel_rmse(out, g["ddim100_first4"]) < 1e-4
