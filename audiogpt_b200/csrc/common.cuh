@@ -1,0 +1,82 @@
+// Common host/device helpers for libagpt_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <stdexcept>
+
+namespace agpt {
+
+// ---- error plumbing: C-ABI functions return int, message kept thread-local ----
+void set_last_error(const std::string& msg);
+
+struct Error : public std::runtime_error {
+  explicit Error(const std::string& m) : std::runtime_error(m) {}
+};
+
+#define AGPT_CUDA(expr)                                                              \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      throw ::agpt::Error(std::string(#expr) + ": " + cudaGetErrorString(_e) +      \
+                          " @" + __FILE__ + ":" + std::to_string(__LINE__));         \
+    }                                                                                \
+  } while (0)
+
+#define AGPT_CHECK(cond, msg)                                                        \
+  do {                                                                               \
+    if (!(cond)) throw ::agpt::Error(std::string("check failed: ") + #cond + ": " + (msg)); \
+  } while (0)
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline long cdivl(long a, long b) { return (a + b - 1) / b; }
+inline int round_up(int a, int b) { return cdiv(a, b) * b; }
+
+// ---- device memory owned by a handle -----------------------------------------
+struct DevBuf {
+  float* p = nullptr;
+  size_t n = 0;  // floats
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { if (p) cudaFree(p); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { if (p) cudaFree(p); }
+  // grow-only; contents are NOT preserved
+  float* ensure(size_t floats) {
+    if (floats > n) {
+      if (p) { cudaDeviceSynchronize(); cudaFree(p); p = nullptr; }
+      AGPT_CUDA(cudaMalloc(&p, floats * sizeof(float)));
+      n = floats;
+    }
+    return p;
+  }
+  void upload(const std::vector<float>& h) {
+    ensure(h.size());
+    AGPT_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+};
+
+// Base of every opaque handle handed across the C ABI.
+struct Handle {
+  uint32_t magic = 0;
+  int device = 0;
+  virtual ~Handle() {}
+};
+constexpr uint32_t kMagicHifigan = 0x48494649;  // 'HIFI'
+constexpr uint32_t kMagicDiffnet = 0x44494646;  // 'DIFF'
+constexpr uint32_t kMagicUnet = 0x554e4554;     // 'UNET'
+
+// ---- small device functions --------------------------------------------------
+__device__ __forceinline__ float lrelu(float x, float a) { return x > 0.f ? x : a * x; }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float siluf_(float x) { return x / (1.f + expf(-x)); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+}  // namespace agpt

@@ -1,0 +1,297 @@
+// HiFi-GAN generator on sm_100a: host driver + the small non-contraction kernels.
+// Arithmetic follows NeuralSeq/modules/hifigan/hifigan.py:144-169 (reference) and is
+// parity-checked against oracle/hifigan_ref.py in tests/test_hifigan_gpu.py.
+#include "common.cuh"
+#include "tapconv.cuh"
+#include "models.h"
+
+namespace agpt {
+
+// [B][C][T] (channels-first, as the reference passes mel) -> [B][T][C] rows
+__global__ void cf_to_cl_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* ib = in + (long)b * C * T;
+  float* ob = out + (long)b * C * T;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < T) ? ib[(long)c * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < T && c < C) ob[(long)t * C + c] = tile[threadIdx.x][i];
+  }
+}
+
+void launch_cf_to_cl(const float* in, float* out, int B, int C, int T, cudaStream_t st) {
+  dim3 grid(cdiv(T, 32), cdiv(C, 32), B), block(32, 8);
+  cf_to_cl_kernel<<<grid, block, 0, st>>>(in, out, C, T);
+  count_launch(1);
+  AGPT_CUDA(cudaGetLastError());
+}
+
+// conv_post: leaky_relu(0.01) -> Conv1d(C -> c_out, k7, pad 3) -> tanh   (hifigan.py:165-167)
+// in [B][L][C] rows, out [B][c_out][L].  Memory-bound (C*4 bytes in per sample out).
+__global__ void conv_post_kernel(const float* __restrict__ in, const float* __restrict__ w /*[c_out][7][C]*/,
+                                 const float* __restrict__ bias, float* __restrict__ out,
+                                 int L, int C, int c_out, float slope) {
+  extern __shared__ float ws[];
+  for (int i = threadIdx.x; i < c_out * 7 * C; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= L) return;
+  const float* ib = in + (long)b * L * C;
+  for (int oc = 0; oc < c_out; ++oc) {
+    float acc = bias[oc];
+    const float* wo = ws + oc * 7 * C;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const long q = p + k - 3;
+      if (q < 0 || q >= L) continue;
+      const float4* row = reinterpret_cast<const float4*>(ib + q * C);
+      const float* wk = wo + k * C;
+      for (int c4 = 0; c4 < C / 4; ++c4) {
+        const float4 x = __ldg(row + c4);
+        acc = fmaf(lrelu(x.x, slope), wk[4 * c4 + 0], acc);
+        acc = fmaf(lrelu(x.y, slope), wk[4 * c4 + 1], acc);
+        acc = fmaf(lrelu(x.z, slope), wk[4 * c4 + 2], acc);
+        acc = fmaf(lrelu(x.w, slope), wk[4 * c4 + 3], acc);
+      }
+    }
+    out[((long)b * c_out + oc) * L + p] = tanhf(acc);
+  }
+}
+
+// NSF excitation add: x[b][p][c] += bias[c] + sum_k w[c][k] * har[b][p*st - pad + k]   (hifigan.py:155-157)
+__global__ void nsf_add_kernel(float* __restrict__ x, const float* __restrict__ har, const float* __restrict__ w,
+                               const float* __restrict__ bias, int L, int C, int Lh, int K, int st, int pad) {
+  const int b = blockIdx.z;
+  const int p = blockIdx.x * blockDim.y + threadIdx.y;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (p >= L || c >= C) return;
+  const float* hb = har + (long)b * Lh;
+  float acc = bias[c];
+  const int base = p * st - pad;
+  for (int k = 0; k < K; ++k) {
+    const int q = base + k;
+    if (q >= 0 && q < Lh) acc = fmaf(w[c * K + k], hb[q], acc);
+  }
+  x[((long)b * L + p) * C + c] += acc;
+}
+
+struct ResBlockW {
+  int ks = 0;
+  std::vector<int> dil;
+  std::vector<PackedConv> c1, c2;  // c2 empty for ResBlock2
+};
+
+struct NoiseConvW {
+  DevBuf w, b;
+  int K = 0, st = 1, pad = 0, C = 0;
+};
+
+struct Hifigan : Handle {
+  agpt_hifigan_cfg cfg;
+  PackedConv conv_pre;
+  std::vector<PackedConv> ups;
+  std::vector<ResBlockW> rbs;
+  std::vector<NoiseConvW> noise;
+  DevBuf post_w, post_b;
+  int c_last = 0, hop = 1;
+  DevBuf melT, buf[6];
+  DevBuf io_mel, io_wav, io_har;  // staging for the host-buffer entry point
+  float* pin_mel = nullptr; float* pin_wav = nullptr; size_t pin_mel_n = 0, pin_wav_n = 0;
+  cudaStream_t own_stream = nullptr;
+
+  ~Hifigan() override {
+    if (pin_mel) cudaFreeHost(pin_mel);
+    if (pin_wav) cudaFreeHost(pin_wav);
+    if (own_stream) cudaStreamDestroy(own_stream);
+  }
+
+  void forward(const float* mel, const float* har, int B, int T, float* wav, cudaStream_t st) {
+    AGPT_CHECK(B >= 1 && T >= 1, "empty batch");
+    const int C0 = cfg.upsample_initial_channel;
+    // buffer sizing: max over stages of L_i * C_i
+    size_t mx = (size_t)T * C0;
+    {
+      long L = T; int C = C0;
+      for (int i = 0; i < cfg.num_upsamples; ++i) { L *= cfg.upsample_rates[i]; C /= 2; mx = std::max(mx, (size_t)L * C); }
+    }
+    mx *= (size_t)B;
+    for (auto& b : buf) b.ensure(mx);
+    melT.ensure((size_t)B * T * cfg.n_mels);
+    float *cur = buf[0].p, *acc = buf[1].p, *X = buf[2].p, *A = buf[3].p, *R0 = buf[4].p, *R1 = buf[5].p;
+
+    launch_cf_to_cl(mel, melT.p, B, cfg.n_mels, T, st);
+    {
+      TapConvParams P = tapconv_params(conv_pre, B, T, 0, 1);
+      P.in = melT.p; P.in_gstride = (long)T * cfg.n_mels; P.in_pitch = cfg.n_mels;
+      P.out = cur; P.out_gstride = (long)T * C0; P.out_pitch = C0;
+      P.pro = PRO_NONE; P.epi = EPI_BIAS;
+      tapconv_launch(P, st);
+    }
+    long L = T; int C = C0;
+    const float inv_nk = 1.f / (float)cfg.num_kernels;
+    for (int i = 0; i < cfg.num_upsamples; ++i) {
+      const int u = cfg.upsample_rates[i];
+      const int Co = C / 2;
+      {  // leaky_relu(0.1) -> ConvTranspose1d   (hifigan.py:153-154)
+        TapConvParams P = tapconv_params(ups[i], B, (int)L, 0, 1);
+        P.in = cur; P.in_gstride = L * C; P.in_pitch = C;
+        P.out = X; P.out_gstride = L * u * Co; P.out_pitch = u * Co;
+        P.pro = PRO_LRELU; P.slope = 0.1f; P.epi = EPI_BIAS;
+        tapconv_launch(P, st);
+      }
+      L *= u; C = Co;
+      if (har) {
+        AGPT_CHECK(cfg.use_nsf, "har_source given but the generator has no noise_convs");
+        const NoiseConvW& nc = noise[i];
+        dim3 block(32, 8), grid(cdiv((int)L, 8), cdiv(C, 32), B);
+        nsf_add_kernel<<<grid, block, 0, st>>>(X, har, nc.w.p, nc.b.p, (int)L, C, T * hop, nc.K, nc.st, nc.pad);
+        count_launch(1);
+        AGPT_CUDA(cudaGetLastError());
+      }
+      const long gs = L * C;
+      for (int j = 0; j < cfg.num_kernels; ++j) {
+        const ResBlockW& rb = rbs[i * cfg.num_kernels + j];
+        const float* x = X;
+        const int nd = (int)rb.dil.size();
+        for (int n = 0; n < nd; ++n) {
+          const bool last = (n == nd - 1);
+          float* dst = last ? acc : ((n & 1) ? R1 : R0);
+          const float* conv_in = x;
+          if (cfg.resblock_type == 1) {
+            TapConvParams P = tapconv_params(rb.c1[n], B, (int)L, 0, rb.dil[n]);
+            P.in = x; P.in_gstride = gs; P.in_pitch = C;
+            P.out = A; P.out_gstride = gs; P.out_pitch = C;
+            P.pro = PRO_LRELU; P.slope = 0.1f; P.epi = EPI_BIAS;
+            tapconv_launch(P, st);
+            conv_in = A;
+          }
+          const PackedConv& pc = (cfg.resblock_type == 1) ? rb.c2[n] : rb.c1[n];
+          TapConvParams P = tapconv_params(pc, B, (int)L, 0, (cfg.resblock_type == 1) ? 1 : rb.dil[n]);
+          P.in = conv_in; P.in_gstride = gs; P.in_pitch = C;
+          P.out = dst; P.out_gstride = gs; P.out_pitch = C;
+          P.pro = PRO_LRELU; P.slope = 0.1f;
+          P.res = x; P.res_gstride = gs; P.res_pitch = C;
+          if (last) { P.epi = EPI_ACC; P.scale = inv_nk; P.accumulate = (j > 0); }
+          else P.epi = EPI_RES;
+          tapconv_launch(P, st);
+          x = dst;
+        }
+      }
+      std::swap(cur, acc);
+    }
+    {
+      const int threads = 256;
+      dim3 grid(cdiv((int)L, threads), B);
+      const size_t smem = (size_t)cfg.c_out * 7 * C * sizeof(float);
+      conv_post_kernel<<<grid, threads, smem, st>>>(cur, post_w.p, post_b.p, wav, (int)L, C, cfg.c_out, 0.01f);
+      count_launch(1);
+      AGPT_CUDA(cudaGetLastError());
+    }
+  }
+};
+
+Handle* hifigan_create(const agpt_hifigan_cfg* cfg, const float* const* W, int nW, int device) {
+  AGPT_CUDA(cudaSetDevice(device));
+  auto* h = new Hifigan();
+  h->magic = kMagicHifigan; h->device = device; h->cfg = *cfg;
+  const int nu = cfg->num_upsamples, nk = cfg->num_kernels;
+  AGPT_CHECK(nu >= 1 && nu <= AGPT_MAX_UPS && nk >= 1 && nk <= AGPT_MAX_RBK, "bad config");
+  int idx = 0;
+  auto next = [&]() -> const float* { AGPT_CHECK(idx < nW, "too few weight arrays"); return W[idx++]; };
+  const int C0 = cfg->upsample_initial_channel;
+  { const float* w = next(); const float* b = next(); pack_conv(h->conv_pre, w, b, C0, cfg->n_mels, 7, false); }
+  h->ups.resize(nu);
+  int C = C0; h->hop = 1;
+  for (int i = 0; i < nu; ++i) {
+    const float* w = next(); const float* b = next();
+    const int u = cfg->upsample_rates[i], k = cfg->upsample_kernel_sizes[i];
+    AGPT_CHECK(C % 2 == 0 && (C / 2) % 4 == 0, "channel counts must stay multiples of 4");
+    pack_convtranspose(h->ups[i], w, b, C, C / 2, k, u, (k - u) / 2);
+    C /= 2; h->hop *= u;
+  }
+  h->c_last = C;
+  h->rbs.resize((size_t)nu * nk);
+  C = C0;
+  for (int i = 0; i < nu; ++i) {
+    C /= 2;
+    for (int j = 0; j < nk; ++j) {
+      ResBlockW& rb = h->rbs[i * nk + j];
+      rb.ks = cfg->resblock_kernel_sizes[j];
+      AGPT_CHECK(rb.ks % 2 == 1 && rb.ks <= kMaxTaps, "resblock kernel size must be odd and <= 11");
+      const int nd = cfg->resblock_num_dilations[j];
+      rb.dil.assign(cfg->resblock_dilations[j], cfg->resblock_dilations[j] + nd);
+      rb.c1.resize(nd);
+      for (int n = 0; n < nd; ++n) { const float* w = next(); const float* b = next(); pack_conv(rb.c1[n], w, b, C, C, rb.ks, false); }
+      if (cfg->resblock_type == 1) {
+        rb.c2.resize(nd);
+        for (int n = 0; n < nd; ++n) { const float* w = next(); const float* b = next(); pack_conv(rb.c2[n], w, b, C, C, rb.ks, false); }
+      }
+    }
+  }
+  {  // conv_post [c_out][C][7] -> [c_out][7][C]
+    const float* w = next(); const float* b = next();
+    std::vector<float> pw((size_t)cfg->c_out * 7 * C);
+    for (int oc = 0; oc < cfg->c_out; ++oc)
+      for (int c = 0; c < C; ++c)
+        for (int k = 0; k < 7; ++k) pw[((size_t)oc * 7 + k) * C + c] = w[((size_t)oc * C + c) * 7 + k];
+    h->post_w.upload(pw);
+    h->post_b.upload(std::vector<float>(b, b + cfg->c_out));
+  }
+  if (cfg->use_nsf) {
+    next(); next();  // m_source.l_linear.{weight,bias}: the source module stays on the host side (RNG)
+    h->noise.resize(nu);
+    int Cc = C0;
+    for (int i = 0; i < nu; ++i) {
+      Cc /= 2;
+      NoiseConvW& nc = h->noise[i];
+      nc.C = Cc;
+      if (i + 1 < nu) {
+        int stv = 1; for (int q = i + 1; q < nu; ++q) stv *= cfg->upsample_rates[q];
+        nc.st = stv; nc.K = 2 * stv; nc.pad = stv / 2;
+      } else { nc.st = 1; nc.K = 1; nc.pad = 0; }
+      const float* w = next(); const float* b = next();
+      nc.w.upload(std::vector<float>(w, w + (size_t)Cc * nc.K));
+      nc.b.upload(std::vector<float>(b, b + Cc));
+    }
+  }
+  AGPT_CHECK(idx == nW, "weight array count does not match the config");
+  return h;
+}
+
+void hifigan_forward(Handle* hh, const float* mel, const float* har, int B, int T, float* wav, cudaStream_t st) {
+  auto* h = static_cast<Hifigan*>(hh);
+  AGPT_CUDA(cudaSetDevice(h->device));
+  h->forward(mel, har, B, T, wav, st);
+}
+
+void hifigan_vocode_host(Handle* hh, const float* mel_host, const float* har_host, int B, int T, float* wav_host) {
+  auto* h = static_cast<Hifigan*>(hh);
+  AGPT_CUDA(cudaSetDevice(h->device));
+  if (!h->own_stream) AGPT_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  const size_t nmel = (size_t)B * h->cfg.n_mels * T, nwav = (size_t)B * h->cfg.c_out * T * h->hop;
+  const size_t nhar = (size_t)B * T * h->hop;
+  if (h->pin_mel_n < nmel) { if (h->pin_mel) cudaFreeHost(h->pin_mel); AGPT_CUDA(cudaMallocHost(&h->pin_mel, nmel * 4)); h->pin_mel_n = nmel; }
+  if (h->pin_wav_n < nwav) { if (h->pin_wav) cudaFreeHost(h->pin_wav); AGPT_CUDA(cudaMallocHost(&h->pin_wav, nwav * 4)); h->pin_wav_n = nwav; }
+  h->io_mel.ensure(nmel); h->io_wav.ensure(nwav);
+  memcpy(h->pin_mel, mel_host, nmel * 4);
+  cudaStream_t st = h->own_stream;
+  AGPT_CUDA(cudaMemcpyAsync(h->io_mel.p, h->pin_mel, nmel * 4, cudaMemcpyHostToDevice, st));
+  const float* har_dev = nullptr;
+  if (har_host) {
+    h->io_har.ensure(nhar);
+    AGPT_CUDA(cudaMemcpyAsync(h->io_har.p, har_host, nhar * 4, cudaMemcpyHostToDevice, st));
+    har_dev = h->io_har.p;
+  }
+  h->forward(h->io_mel.p, har_dev, B, T, h->io_wav.p, st);
+  AGPT_CUDA(cudaMemcpyAsync(h->pin_wav, h->io_wav.p, nwav * 4, cudaMemcpyDeviceToHost, st));
+  AGPT_CUDA(cudaStreamSynchronize(st));
+  memcpy(wav_host, h->pin_wav, nwav * 4);
+}
+
+}  // namespace agpt

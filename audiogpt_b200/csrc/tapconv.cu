@@ -1,0 +1,250 @@
+// tapconv kernel (fp32 FMA) + launcher.  See tapconv.cuh for the contract.
+#include "tapconv.cuh"
+#include "models.h"
+
+namespace agpt {
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+
+__device__ __forceinline__ void tc_epilogue(const TapConvParams& P, int g, int p, int co, float4 v) {
+  if (co >= P.Cout) return;
+  if (P.bias) {
+    const float4 b = *reinterpret_cast<const float4*>(P.bias + co);
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  }
+  switch (P.epi) {
+    case EPI_BIAS: break;
+    case EPI_RES:
+    case EPI_ACC: {
+      if (P.res) {
+        const float4 r = *reinterpret_cast<const float4*>(P.res + g * P.res_gstride + (long)p * P.res_pitch + co);
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      }
+      if (P.epi == EPI_ACC) {
+        v.x *= P.scale; v.y *= P.scale; v.z *= P.scale; v.w *= P.scale;
+        if (P.accumulate) {
+          const float4 o = *reinterpret_cast<const float4*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + co);
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+      }
+      break;
+    }
+    case EPI_RELU:
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+      break;
+    case EPI_TANH:
+      v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w);
+      break;
+    case EPI_ADDVEC: {
+      const float4 e = *reinterpret_cast<const float4*>(P.evec + (long)g * P.evec_gstride + co);
+      v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+      break;
+    }
+    case EPI_GATE:
+    case EPI_GEGLU: {
+      if (P.res) {  // pre-activation additive term (DiffNet hoisted conditioner projection)
+        const float4 r = *reinterpret_cast<const float4*>(P.res + g * P.res_gstride + (long)p * P.res_pitch + co);
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      }
+      float2 o;
+      if (P.epi == EPI_GATE) {
+        o.x = sigmoidf_(v.x) * tanhf(v.y);
+        o.y = sigmoidf_(v.z) * tanhf(v.w);
+      } else {
+        o.x = v.x * gelu_erf(v.y);
+        o.y = v.z * gelu_erf(v.w);
+      }
+      *reinterpret_cast<float2*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + (co >> 1)) = o;
+      return;
+    }
+    case EPI_DIFFOUT: {
+      if (co < P.csplit) {
+        float4* o = reinterpret_cast<float4*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + co);
+        float4 x = *o;
+        const float r2 = 0.70710678118654752440f;
+        x.x = (x.x + v.x) * r2; x.y = (x.y + v.y) * r2; x.z = (x.z + v.z) * r2; x.w = (x.w + v.w) * r2;
+        *o = x;
+      } else {
+        float4* o = reinterpret_cast<float4*>(P.out2 + g * P.out2_gstride + (long)p * P.out2_pitch + (co - P.csplit));
+        if (P.accumulate) {
+          float4 s = *o;
+          v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
+        }
+        *o = v;
+      }
+      return;
+    }
+    case EPI_STORE_CF: {
+      float* o = P.out + g * P.out_gstride + (long)co * P.L + p;
+      o[0] = v.x;
+      if (co + 1 < P.Cout) o[(long)P.L] = v.y;
+      if (co + 2 < P.Cout) o[2 * (long)P.L] = v.z;
+      if (co + 3 < P.Cout) o[3 * (long)P.L] = v.w;
+      return;
+    }
+    default: break;
+  }
+  *reinterpret_cast<float4*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + co) = v;
+}
+
+template <int BN>
+__global__ void __launch_bounds__((BN / 8) * 16, (BN == 128 ? 2 : (BN == 64 ? 4 : 6)))
+tapconv_kernel(const __grid_constant__ TapConvParams P) {
+  constexpr int NTX = BN / 8, NT = NTX * 16, KC = TC_KC, BM = TC_BM;
+  extern __shared__ __align__(16) float smem[];
+  const int R = P.R;
+  int* rowaddr = reinterpret_cast<int*>(smem);
+  float* Xs = smem + (R + 8);
+  float* Ws = Xs + 4 * KC * R;
+
+  const int tid = threadIdx.x, tx = tid % NTX, ty = tid / NTX;
+  const int g = blockIdx.z, co0 = blockIdx.y * BN, q0 = blockIdx.x * BM;
+  const int Wv = P.Wreal > 0 ? P.Wreal + 1 : 0;
+  const int Lv = Wv ? (P.L / P.Wreal) * Wv : P.L;
+
+  for (int i = tid; i < R + 8; i += NT) {
+    const int q = q0 + P.lo_al + i;
+    int a = -1;
+    if (q >= 0 && q < Lv) {
+      if (Wv) {
+        const int h = q / Wv, w = q - h * Wv;
+        if (w < P.Wreal) a = (h * P.Wreal + w) * P.in_pitch;
+      } else {
+        a = q * P.in_pitch;
+      }
+    }
+    rowaddr[i] = a;
+  }
+
+  const float* __restrict__ ing = P.in + g * P.in_gstride;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int nchunks = P.cin_pad / KC, total = nchunks * P.ntaps;
+
+  auto issue_w = [&](int it) {
+    const int chunk = it / P.ntaps, tap = it - chunk * P.ntaps;
+    const int ci = tid / (BN / 4), c4 = (tid % (BN / 4)) * 4;
+    float* dst = Ws + (it & 1) * KC * BN + ci * BN + c4;
+    if (co0 + c4 < P.cout_pad) {
+      const float* src = P.w + ((long)(tap * P.cin_pad + chunk * KC + ci)) * P.cout_pad + co0 + c4;
+      cp_async16(dst, src);
+    } else {
+      *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    cp_async_commit();
+  };
+
+  issue_w(0);
+  int it = 0;
+  for (int chunk = 0; chunk < nchunks; ++chunk) {
+    __syncthreads();  // rowaddr ready (first) / everyone done reading Xs of the previous chunk
+    {
+      const int nitems = (R >> 2) * KC;
+      for (int item = tid; item < nitems; item += NT) {
+        const int ci = item % KC, m = item / KC;
+        const int c = chunk * KC + ci;
+        const bool cok = c < P.Cin;
+        const int4 a0 = *reinterpret_cast<const int4*>(rowaddr + 4 * m);
+        const int4 a1 = *reinterpret_cast<const int4*>(rowaddr + 4 * m + 4);
+        const int aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        float pv = 0.f;
+        if (P.pro == PRO_ADDVEC && cok) pv = P.pvec[(long)g * P.pvec_gstride + c];
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float x = 0.f;
+          if (cok && aa[i] >= 0) {
+            x = __ldg(ing + aa[i] + c);
+            if (P.pro == PRO_LRELU) x = lrelu(x, P.slope);
+            else if (P.pro == PRO_ADDVEC) x += pv;
+            else if (P.pro == PRO_SILU) x = siluf_(x);
+          }
+          v[i] = x;
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          *reinterpret_cast<float4*>(Xs + (s * KC + ci) * R + 4 * m) = make_float4(v[s], v[s + 1], v[s + 2], v[s + 3]);
+      }
+    }
+    for (int tap = 0; tap < P.ntaps; ++tap, ++it) {
+      cp_async_wait_all();
+      __syncthreads();  // W(it) + Xs visible; everyone finished compute(it-1)
+      if (it + 1 < total) issue_w(it + 1);
+      const int e = P.tap_off[tap] - P.lo_al;
+      const float* xs = Xs + (e & 3) * KC * R + (e & ~3) + ty * 4;
+      const float* ws = Ws + (it & 1) * KC * BN + tx * 4;
+#pragma unroll
+      for (int ci = 0; ci < KC; ++ci) {
+        const float4 xa = *reinterpret_cast<const float4*>(xs + ci * R);
+        const float4 xb = *reinterpret_cast<const float4*>(xs + ci * R + 64);
+        const float4 wa = *reinterpret_cast<const float4*>(ws + ci * BN);
+        const float4 wb = *reinterpret_cast<const float4*>(ws + ci * BN + BN / 2);
+        const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+      }
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + (i - 4));
+    const int q = q0 + r;
+    if (q >= Lv) continue;
+    int p = q;
+    if (Wv) {
+      const int h = q / Wv, w = q - h * Wv;
+      if (w >= P.Wreal) continue;
+      p = h * P.Wreal + w;
+    }
+    tc_epilogue(P, g, p, co0 + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+    tc_epilogue(P, g, p, co0 + BN / 2 + tx * 4, make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
+  }
+}
+
+
+// Fill geometry-dependent fields (offsets, halo, smem rows) and launch.
+void tapconv_launch(TapConvParams P, cudaStream_t st) {
+  AGPT_CHECK(P.ntaps >= 1 && P.ntaps <= kMaxTaps, "ntaps");
+  AGPT_CHECK(P.cin_pad % TC_KC == 0 && P.cout_pad % 4 == 0, "padding");
+  AGPT_CHECK(P.in_pitch % 1 == 0 && (P.epi == EPI_STORE_CF || P.out_pitch % (P.epi == EPI_GATE || P.epi == EPI_GEGLU ? 2 : 4) == 0), "pitch");
+  int lo = P.tap_off[0], hi = P.tap_off[0];
+  for (int t = 1; t < P.ntaps; ++t) { lo = min(lo, P.tap_off[t]); hi = max(hi, P.tap_off[t]); }
+  P.lo_al = (lo >= 0) ? (lo / 4) * 4 : -(((-lo) + 3) / 4) * 4;
+  int R = round_up(TC_BM + (hi - P.lo_al), 4);
+  while (R % 32 != 4) R += 4;
+  P.R = R;
+  const int Wv = P.Wreal > 0 ? P.Wreal + 1 : 0;
+  const int Lv = Wv ? (P.L / P.Wreal) * Wv : P.L;
+  const int bn = tc_pick_bn(P.Cout);
+  const size_t smem = ((size_t)(R + 8) + 4 * TC_KC * (size_t)R + 2 * TC_KC * (size_t)bn) * sizeof(float);
+  dim3 grid(cdiv(Lv, TC_BM), cdiv(P.Cout, bn), P.G);
+  static bool attr_done = false;
+  if (!attr_done) {
+    AGPT_CUDA(cudaFuncSetAttribute(tapconv_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    AGPT_CUDA(cudaFuncSetAttribute(tapconv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    AGPT_CUDA(cudaFuncSetAttribute(tapconv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_done = true;
+  }
+  AGPT_CHECK(smem <= 100 * 1024, "tapconv smem too large (image too wide?)");
+  if (bn == 128) tapconv_kernel<128><<<grid, 256, smem, st>>>(P);
+  else if (bn == 64) tapconv_kernel<64><<<grid, 128, smem, st>>>(P);
+  else tapconv_kernel<32><<<grid, 64, smem, st>>>(P);
+  count_launch(1);
+  AGPT_CUDA(cudaGetLastError());
+}
+
+
+}  // namespace agpt

@@ -1,0 +1,165 @@
+// tapconv: the one contraction primitive of the hot path (fp32 FMA version).
+//
+//   out[g, p, co] = epi( bias[co] + sum_tap sum_ci  pro(in[g, p (+) off_tap, ci]) * W[tap][ci][co] )
+//
+// Activations are CHANNELS-LAST rows ([G][L][C], C contiguous), so a conv tap is a
+// row shift, a Linear is the 1-tap case, a 3x3 conv is 9 taps over a "virtual"
+// flat grid of width W+1 (one shared zero column => no per-tap masks), and
+// ConvTranspose1d(k=2u, stride u) is a 3-tap conv producing u*Cout channels whose
+// [L][u*Cout] output *is* the [u*L][Cout] upsampled tensor.
+//
+// Replaces (reference call sites): F.conv1d / F.conv_transpose1d in
+// NeuralSeq/modules/hifigan/hifigan.py:54-61,151-167 and modules/diff/net.py:66-78,107-130;
+// F.conv2d / F.linear in ldm/modules/diffusionmodules/openaimodel.py:255-275,711-744 and
+// ldm/modules/attention.py:37-64,170-193,250-261.
+//
+// Tiling: CTA = 128 rows x BN cols (BN in {32,64,128}), 8x8 register micro-tile per
+// thread, K-loop over (8-channel chunk) x tap.  The activation tile (+halo) is staged
+// ONCE per chunk in shared memory in four row-shifted copies so that every tap is read
+// with aligned 128-bit LDS; weight slabs [8][BN] stream through a cp.async double buffer.
+#pragma once
+#include "common.cuh"
+
+namespace agpt {
+
+constexpr int kMaxTaps = 12;
+constexpr int TC_BM = 128;
+constexpr int TC_KC = 8;
+
+enum Pro : int { PRO_NONE = 0, PRO_LRELU = 1, PRO_ADDVEC = 2, PRO_SILU = 3 };
+enum Epi : int {
+  EPI_BIAS = 0,     // v + bias
+  EPI_RES = 1,      // v + bias + res[g,p,co]
+  EPI_ACC = 2,      // out = (accumulate ? out : 0) + scale * (v + bias + res)
+  EPI_RELU = 3,     // relu(v + bias)
+  EPI_ADDVEC = 4,   // v + bias + evec[g,co]
+  EPI_GATE = 5,     // interleaved (gate,filter) pairs: sigmoid(g)*tanh(f), + aux[g,p,co] before; out has Cout/2 channels
+  EPI_GEGLU = 6,    // interleaved (a,gate) pairs: a*gelu(gate); out has Cout/2 channels
+  EPI_DIFFOUT = 7,  // co<csplit: out=(out+v)*rsqrt2 in place ; else out2 (+)= v
+  EPI_STORE_CF = 8, // channels-first store out[g][co][p]
+  EPI_TANH = 9,     // tanh(v + bias)
+};
+
+struct TapConvParams {
+  const float* in; long in_gstride; int in_pitch;
+  const float* w;      // packed [ntaps][cin_pad][cout_pad]
+  const float* bias;   // [cout_pad] or nullptr
+  float* out; long out_gstride; int out_pitch;
+  int G, L, Wreal, Cin, cin_pad, Cout, cout_pad;
+  int ntaps; int tap_off[kMaxTaps];
+  int lo_al, R;
+  int pro; float slope; const float* pvec; int pvec_gstride;
+  int epi; const float* res; long res_gstride; int res_pitch; float scale; int accumulate;
+  const float* evec; int evec_gstride;
+  float* out2; long out2_gstride; int out2_pitch; int csplit;
+};
+
+// ---------------------------------------------------------------- host side
+struct PackedConv {
+  DevBuf w, b;
+  int Cin = 0, cin_pad = 0, Cout = 0, cout_pad = 0, ntaps = 0;
+  int tap_off_1d[kMaxTaps] = {0};   // for 1-D convs: row offsets; 2-D convs derive offsets from W at launch
+  bool is2d = false;
+  bool has_bias = false;
+};
+
+inline int tc_pick_bn(int cout) {
+  if (cout <= 32) return 32;
+  if (cout <= 64) return 64;
+  const int w128 = round_up(cout, 128), w64 = round_up(cout, 64);
+  return (w128 <= w64) ? 128 : 64;
+}
+
+// Fill geometry-dependent fields (offsets, halo, smem rows) and launch (tapconv.cu).
+void tapconv_launch(TapConvParams P, cudaStream_t st);
+
+// Common setup from a PackedConv; caller fills in/out/pro/epi afterwards.
+inline TapConvParams tapconv_params(const PackedConv& pc, int G, int L, int Wreal, int dil) {
+  TapConvParams P;
+  memset(&P, 0, sizeof(P));
+  P.w = pc.w.p;
+  P.bias = pc.has_bias ? pc.b.p : nullptr;
+  P.G = G; P.L = L; P.Wreal = Wreal;
+  P.Cin = pc.Cin; P.cin_pad = pc.cin_pad; P.Cout = pc.Cout; P.cout_pad = pc.cout_pad;
+  P.ntaps = pc.ntaps;
+  if (pc.is2d) {
+    AGPT_CHECK(pc.ntaps == 9 && Wreal > 0, "2d conv needs W");
+    const int Wv = Wreal + 1;
+    for (int dh = -1, t = 0; dh <= 1; ++dh)
+      for (int dw = -1; dw <= 1; ++dw, ++t) P.tap_off[t] = dh * Wv + dw;
+  } else {
+    for (int t = 0; t < pc.ntaps; ++t) P.tap_off[t] = pc.tap_off_1d[t] * dil;
+  }
+  P.scale = 1.f;
+  return P;
+}
+
+// ---- host-side weight packing (reference layouts -> [tap][cin_pad][cout_pad]) ----
+// Conv1d / Conv2d weight [Cout][Cin][K...] (torch layout), "same" padding, odd K.
+inline void pack_conv(PackedConv& pc, const float* w, const float* b, int Cout, int Cin, int K, bool is2d,
+                      float wscale = 1.f) {
+  pc.Cin = Cin; pc.Cout = Cout; pc.cin_pad = round_up(Cin, TC_KC); pc.cout_pad = round_up(Cout, 32);
+  pc.ntaps = K; pc.is2d = is2d;
+  std::vector<float> h((size_t)K * pc.cin_pad * pc.cout_pad, 0.f);
+  for (int co = 0; co < Cout; ++co)
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int k = 0; k < K; ++k)
+        h[((size_t)k * pc.cin_pad + ci) * pc.cout_pad + co] = w[((size_t)co * Cin + ci) * K + k] * wscale;
+  pc.w.upload(h);
+  if (!is2d) {
+    const int c = (K - 1) / 2;
+    for (int k = 0; k < K; ++k) pc.tap_off_1d[k] = k - c;
+  }
+  pc.has_bias = b != nullptr;
+  std::vector<float> hb(pc.cout_pad, 0.f);
+  if (b) for (int co = 0; co < Cout; ++co) hb[co] = b[co];
+  pc.b.upload(hb);
+}
+
+// Same, but output channels interleaved (co -> 2*(co % half) + co / half): used where the
+// epilogue consumes (first-half, second-half) channel pairs (DiffNet gate/filter, GEGLU).
+inline void pack_conv_pairs(PackedConv& pc, const float* w, const float* b, int Cout, int Cin, int K) {
+  const int half = Cout / 2;
+  std::vector<float> w2((size_t)Cout * Cin * K), b2(Cout, 0.f);
+  for (int co = 0; co < Cout; ++co) {
+    const int dst = 2 * (co % half) + co / half;
+    memcpy(&w2[(size_t)dst * Cin * K], &w[(size_t)co * Cin * K], sizeof(float) * Cin * K);
+    if (b) b2[dst] = b[co];
+  }
+  pack_conv(pc, w2.data(), b ? b2.data() : nullptr, Cout, Cin, K, false);
+}
+
+// ConvTranspose1d weight [Cin][Cout][K], stride u, padding pad  ->  taps d in {..-1,0,+1..}
+// over INPUT rows with u*Cout output channels (polyphase form; SURVEY.md 8a kernel cheat sheet).
+inline void pack_convtranspose(PackedConv& pc, const float* w, const float* b, int Cin, int Cout, int K, int u, int pad) {
+  std::vector<int> deltas;
+  for (int d = -8; d <= 8; ++d) {
+    bool any = false;
+    for (int r = 0; r < u && !any; ++r) {
+      const int k = r + pad - d * u;
+      if (k >= 0 && k < K) any = true;
+    }
+    if (any) deltas.push_back(d);
+  }
+  AGPT_CHECK((int)deltas.size() <= kMaxTaps, "convtranspose taps");
+  pc.Cin = Cin; pc.Cout = u * Cout; pc.cin_pad = round_up(Cin, TC_KC); pc.cout_pad = round_up(u * Cout, 32);
+  pc.ntaps = (int)deltas.size(); pc.is2d = false;
+  std::vector<float> h((size_t)pc.ntaps * pc.cin_pad * pc.cout_pad, 0.f);
+  for (int t = 0; t < pc.ntaps; ++t) {
+    pc.tap_off_1d[t] = deltas[t];
+    for (int r = 0; r < u; ++r) {
+      const int k = r + pad - deltas[t] * u;
+      if (k < 0 || k >= K) continue;
+      for (int ci = 0; ci < Cin; ++ci)
+        for (int co = 0; co < Cout; ++co)
+          h[((size_t)t * pc.cin_pad + ci) * pc.cout_pad + r * Cout + co] = w[((size_t)ci * Cout + co) * K + k];
+    }
+  }
+  pc.w.upload(h);
+  pc.has_bias = b != nullptr;
+  std::vector<float> hb(pc.cout_pad, 0.f);
+  if (b) for (int r = 0; r < u; ++r) for (int co = 0; co < Cout; ++co) hb[r * Cout + co] = b[co];
+  pc.b.upload(hb);
+}
+
+}  // namespace agpt

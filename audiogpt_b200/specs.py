@@ -37,11 +37,11 @@ HIFIGAN_V1 = dict(  # NeuralSeq/egs/egs_bases/tts/vocoder/hifigan.yaml:3-12
     audio_sample_rate=22050,
 )
 
-HIFIGAN_SMALL = dict(  # same topology, 16x narrower: CPU-second parity fixture
+HIFIGAN_SMALL = dict(  # same topology, 8x narrower: CPU-second parity fixture
     resblock="1",
     upsample_rates=[8, 8, 2, 2],
     upsample_kernel_sizes=[16, 16, 4, 4],
-    upsample_initial_channel=32,
+    upsample_initial_channel=64,
     resblock_kernel_sizes=[3, 7, 11],
     resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]],
     use_pitch_embed=False,

@@ -1,0 +1,147 @@
+/* libagpt_b200 -- C ABI of the B200-native AudioGPT generative back-end.
+ *
+ * The reference (AIGC-Audio/AudioGPT) is pure Python: it has no FFI layer, its
+ * "plugin boundary" is the Python class surface listed in SURVEY.md 8(b).  The
+ * drop-in Python classes in audiogpt_b200/ bind these entry points through
+ * ctypes (audiogpt_b200/_lib.py); INTEGRATION.md shows the stub.  Each entry
+ * point cites the reference interface it replaces.
+ *
+ * Conventions: every function returns 0 on success, non-zero on error with a
+ * thread-local message retrievable through agpt_last_error().  Device pointers
+ * are plain fp32 arrays, valid for the stream-ordered duration of the call;
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ * Weights are copied and re-laid-out at create time (the handle owns them).
+ * One handle per device; a handle is not re-entrant.  There is no CPU fallback.
+ */
+#ifndef AGPT_B200_H
+#define AGPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct agpt_handle_s* agpt_handle;
+
+const char* agpt_last_error(void);
+int agpt_version(void);
+/* number of kernels launched by this library in this process so far (bench.py's gpu_launches) */
+long long agpt_launch_count(void);
+void agpt_destroy(agpt_handle h);
+
+/* ------------------------------------------------------------------ HiFi-GAN
+ * Replaces HifiGanGenerator.__init__/forward/remove_weight_norm
+ * (NeuralSeq/modules/hifigan/hifigan.py:104-178) and the twin
+ * text_to_audio/Make_An_Audio/vocoder/hifigan/modules.py:86-136.            */
+#define AGPT_MAX_UPS 8
+#define AGPT_MAX_RBK 8
+#define AGPT_MAX_DIL 8
+typedef struct {
+  int n_mels;                  /* 80 */
+  int c_out;                   /* 1 */
+  int upsample_initial_channel;
+  int num_upsamples;
+  int upsample_rates[AGPT_MAX_UPS];
+  int upsample_kernel_sizes[AGPT_MAX_UPS];
+  int resblock_type;           /* 1 = ResBlock1 (hifigan.py:30-67), 2 = ResBlock2 (:70-91) */
+  int num_kernels;
+  int resblock_kernel_sizes[AGPT_MAX_RBK];
+  int resblock_num_dilations[AGPT_MAX_RBK];
+  int resblock_dilations[AGPT_MAX_RBK][AGPT_MAX_DIL];
+  int use_nsf;                 /* h['use_pitch_embed']: noise_convs present (hifigan.py:111-132) */
+} agpt_hifigan_cfg;
+
+/* host_weights: fp32 HOST arrays in the key order of
+ * audiogpt_b200.specs.hifigan_param_shapes(h) (weight-norm already folded;
+ * m_source.l_linear.* entries are skipped by the library).                   */
+int agpt_hifigan_create(const agpt_hifigan_cfg* cfg, const float* const* host_weights,
+                        int n_weights, int device, agpt_handle* out);
+/* mel [B,n_mels,T] (device) -> wav [B,c_out,T*prod(rates)] (device).
+ * har_source: NULL or the merged NSF excitation [B,1,T*prod(rates)] (device),
+ * i.e. SourceModuleHnNSF's first output (hifigan.py:145-149).                */
+int agpt_hifigan_forward(agpt_handle h, const float* mel, const float* har_source,
+                         int B, int T, float* wav, void* stream);
+/* Same through HOST buffers: H2D copy, forward, D2H copy, synchronise.
+ * This is what HifiGAN.spec2wav (NeuralSeq/vocoders/hifigan.py:55-69) calls. */
+int agpt_hifigan_vocode_host(agpt_handle h, const float* mel_host, const float* har_host,
+                             int B, int T, float* wav_host);
+
+/* ------------------------------------------------------------------ DiffNet + GaussianDiffusion
+ * Replaces DiffNet.forward (NeuralSeq/modules/diff/net.py:107-130) and the
+ * elementwise part of GaussianDiffusion.p_sample / p_sample_plms
+ * (NeuralSeq/modules/diff/shallow_diffusion_tts.py:134-204).                 */
+typedef struct {
+  int in_dims;                 /* 80 mel bins */
+  int hidden_size;             /* encoder_hidden: channels of cond */
+  int residual_layers;
+  int residual_channels;
+  int dilation_cycle_length;
+} agpt_diffnet_cfg;
+
+int agpt_diffnet_create(const agpt_diffnet_cfg* cfg, const float* const* host_weights,
+                        int n_weights, int device, agpt_handle* out);
+/* Hoist the step-invariant conditioner projections of all layers
+ * (net.py:68: conditioner_projection(cond)) for cond [B,hidden,T] (device).  */
+int agpt_diffnet_set_cond(agpt_handle h, const float* cond, int B, int T, void* stream);
+/* eps [B,1,M,T] = DiffNet(x [B,1,M,T], t [B] (host ints), cond set above)    */
+int agpt_diffnet_eps(agpt_handle h, const float* x, const int* t_host, float* eps, void* stream);
+/* x_out = p_sample(x, t, noise) with eps computed internally; coef[b] =
+ * {sqrt_recip_ac, sqrt_recipm1_ac, post_mean_coef1, post_mean_coef2,
+ *  exp(0.5*post_log_var) * (t!=0)} gathered on the host from the fp32 tables
+ * (shallow_diffusion_tts.py:108-123).  clip: clamp x0 to [-1,1] (:153-154).
+ * x_out may alias x.                                                         */
+int agpt_gd_p_sample(agpt_handle h, const float* x, const int* t_host, const float* coef_host /*[B][5]*/,
+                     const float* noise, int clip_denoised, float* x_out, void* stream);
+/* generic elementwise: out = a0*x + a1*e0 + a2*e1 + a3*e2 + a4*e3 (per-sample
+ * coefficient rows coef_host[B][5]; NULL e_i are skipped) -- the PLMS
+ * combinations of shallow_diffusion_tts.py:174-204.                          */
+int agpt_axpby5(const float* x, const float* e0, const float* e1, const float* e2, const float* e3,
+                const float* coef_host, int B, long n_per_sample, float* out, void* stream);
+
+/* ------------------------------------------------------------------ UNet + DDIM
+ * Replaces UNetModel.forward (ldm/modules/diffusionmodules/openaimodel.py:711-744)
+ * and DDIMSampler.p_sample_ddim's arithmetic (ldm/models/diffusion/ddim.py:168-225). */
+#define AGPT_MAX_LEVELS 8
+typedef struct {
+  int in_channels, out_channels, model_channels;
+  int num_res_blocks;
+  int num_levels;
+  int channel_mult[AGPT_MAX_LEVELS];
+  int attn_at_level[AGPT_MAX_LEVELS];   /* 1 if ds=2^level is in attention_resolutions */
+  int num_heads;                        /* -1 => use num_head_channels */
+  int num_head_channels;
+  int transformer_depth;
+  int context_dim;
+} agpt_unet_cfg;
+
+int agpt_unet_create(const agpt_unet_cfg* cfg, const float* const* host_weights,
+                     int n_weights, int device, agpt_handle* out);
+/* Hoist the step-invariant to_k/to_v(context) of every cross-attention
+ * (attention.py:174-176) for context [N,S,context_dim] (device).             */
+int agpt_unet_set_context(agpt_handle h, const float* context, int N, int S, void* stream);
+/* eps [N,Cout,H,W] = UNet(x [N,Cin,H,W], t [N] host ints, context set above) */
+int agpt_unet_forward(agpt_handle h, const float* x, const int* t_host, int N, int H, int W,
+                      float* eps, void* stream);
+/* One DDIM step with classifier-free guidance on a doubled batch
+ * (ddim.py:177-225): eps2 = [e_uncond ; e_cond] (2B samples), e = e_u + s*(e_c-e_u);
+ * pred_x0 = (x - sqrt_om*e)/sqrt(a_t); x_prev = sqrt(a_prev)*pred_x0 +
+ * sqrt(1-a_prev-sigma^2)*e + sigma*noise*temperature.  If eps2_is_single != 0
+ * eps2 holds B samples and no guidance is applied.                           */
+int agpt_ddim_update(const float* x, const float* eps2, int eps2_is_single, float cfg_scale,
+                     float a_t, float a_prev, float sigma_t, float sqrt_one_minus_at,
+                     const float* noise, float temperature, int B, long n_per_sample,
+                     float* x_prev, float* pred_x0_or_null, void* stream);
+/* Whole DDIM loop on device (ddim.py:117-166) with CFG; context = [uncond ; cond]
+ * set through agpt_unet_set_context (2B rows) or B rows when cfg_scale == 1.
+ * tables: host arrays of length S in *sampling order* (index S-1 first).     */
+int agpt_unet_ddim_sample(agpt_handle h, const float* x_T, int B, int H, int W, int S,
+                          const int* t_steps_host, const float* a_t, const float* a_prev,
+                          const float* sigma, const float* sqrt_om, float cfg_scale,
+                          float* x_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGPT_B200_H */
