@@ -1,6 +1,7 @@
 // extern "C" boundary of libagpt_b200.so (declared in include/agpt_b200.h).
 #include <atomic>
 #include "models.h"
+#include "nn_kernels.h"
 
 namespace agpt {
 static thread_local std::string g_last_error;
@@ -67,6 +68,87 @@ int agpt_hifigan_vocode_host(agpt_handle h, const float* mel_host, const float* 
   return guarded([&] {
     AGPT_CHECK(mel_host && wav_host, "null tensor");
     hifigan_vocode_host(as(h, kMagicHifigan, "hifigan"), mel_host, har_host, B, T, wav_host);
+  });
+}
+
+int agpt_diffnet_create(const agpt_diffnet_cfg* cfg, const float* const* host_weights, int n_weights, int device,
+                        agpt_handle* out) {
+  return guarded([&] {
+    AGPT_CHECK(cfg && host_weights && out, "null argument");
+    *out = reinterpret_cast<agpt_handle>(diffnet_create(cfg, host_weights, n_weights, device));
+  });
+}
+
+int agpt_diffnet_set_cond(agpt_handle h, const float* cond, int B, int T, void* stream) {
+  return guarded([&] { diffnet_set_cond(as(h, kMagicDiffnet, "diffnet"), cond, B, T, (cudaStream_t)stream); });
+}
+
+int agpt_diffnet_eps(agpt_handle h, const float* x, const int* t_host, float* eps, void* stream) {
+  return guarded([&] {
+    AGPT_CHECK(x && t_host && eps, "null argument");
+    diffnet_eps(as(h, kMagicDiffnet, "diffnet"), x, t_host, eps, (cudaStream_t)stream);
+  });
+}
+
+int agpt_gd_p_sample(agpt_handle h_or_null, const float* x, const float* eps_or_null, const int* t_host,
+                     const float* coef_host, const float* noise_or_null, int clip_denoised, int B,
+                     long n_per_sample, float* x_out, void* stream) {
+  return guarded([&] {
+    AGPT_CHECK(x && coef_host && x_out && B >= 1, "null argument");
+    Handle* hh = nullptr;
+    if (!eps_or_null) { AGPT_CHECK(t_host, "t_host required when eps is computed internally"); hh = as(h_or_null, kMagicDiffnet, "diffnet"); }
+    gd_p_sample(hh, x, eps_or_null, t_host, coef_host, noise_or_null, clip_denoised, B, n_per_sample, x_out,
+                (cudaStream_t)stream);
+  });
+}
+
+int agpt_axpby5(const float* x, const float* e0, const float* e1, const float* e2, const float* e3,
+                const float* coef_host, int B, long n_per_sample, float* out, void* stream) {
+  return guarded([&] {
+    AGPT_CHECK(x && coef_host && out && B >= 1, "null argument");
+    axpby5(x, e0, e1, e2, e3, coef_host, B, n_per_sample, out, (cudaStream_t)stream);
+  });
+}
+
+int agpt_unet_create(const agpt_unet_cfg* cfg, const float* const* host_weights, int n_weights, int device,
+                     agpt_handle* out) {
+  return guarded([&] {
+    AGPT_CHECK(cfg && host_weights && out, "null argument");
+    *out = reinterpret_cast<agpt_handle>(unet_create(cfg, host_weights, n_weights, device));
+  });
+}
+
+int agpt_unet_set_context(agpt_handle h, const float* context, int N, int S, void* stream) {
+  return guarded([&] {
+    AGPT_CHECK(context, "null context");
+    unet_set_context(as(h, kMagicUnet, "unet"), context, N, S, (cudaStream_t)stream);
+  });
+}
+
+int agpt_unet_forward(agpt_handle h, const float* x, const int* t_host, int N, int H, int W, float* eps, void* stream) {
+  return guarded([&] {
+    AGPT_CHECK(x && t_host && eps, "null argument");
+    unet_forward(as(h, kMagicUnet, "unet"), x, t_host, N, H, W, eps, (cudaStream_t)stream);
+  });
+}
+
+int agpt_ddim_update(const float* x, const float* eps2, int eps2_is_single, float cfg_scale, float a_t, float a_prev,
+                     float sigma_t, float sqrt_one_minus_at, const float* noise, float temperature, int B,
+                     long n_per_sample, float* x_prev, float* pred_x0_or_null, void* stream) {
+  return guarded([&] {
+    AGPT_CHECK(x && eps2 && x_prev && B >= 1, "null argument");
+    ddim_update(x, eps2, eps2_is_single, cfg_scale, a_t, a_prev, sigma_t, sqrt_one_minus_at, noise, temperature, B,
+                n_per_sample, x_prev, pred_x0_or_null, (cudaStream_t)stream);
+  });
+}
+
+int agpt_unet_ddim_sample(agpt_handle h, const float* x_T, int B, int H, int W, int S, const int* t_steps_host,
+                          const float* a_t, const float* a_prev, const float* sigma, const float* sqrt_om,
+                          float cfg_scale, float* x_out, void* stream) {
+  return guarded([&] {
+    AGPT_CHECK(x_T && t_steps_host && a_t && a_prev && sigma && sqrt_om && x_out && S >= 1, "null argument");
+    unet_ddim_sample(as(h, kMagicUnet, "unet"), x_T, B, H, W, S, t_steps_host, a_t, a_prev, sigma, sqrt_om, cfg_scale,
+                     x_out, (cudaStream_t)stream);
   });
 }
 

@@ -77,6 +77,10 @@ constexpr uint32_t kMagicUnet = 0x554e4554;     // 'UNET'
 __device__ __forceinline__ float lrelu(float x, float a) { return x > 0.f ? x : a * x; }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 __device__ __forceinline__ float siluf_(float x) { return x / (1.f + expf(-x)); }
+__device__ __forceinline__ float mishf_(float x) {
+  const float sp = x > 20.f ? x : log1pf(expf(x));  // F.softplus (beta=1, threshold=20)
+  return x * tanhf(sp);
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
 }  // namespace agpt

@@ -13,4 +13,19 @@ Handle* hifigan_create(const agpt_hifigan_cfg* cfg, const float* const* W, int n
 void hifigan_forward(Handle* h, const float* mel, const float* har, int B, int T, float* wav, cudaStream_t st);
 void hifigan_vocode_host(Handle* h, const float* mel_host, const float* har_host, int B, int T, float* wav_host);
 
+Handle* diffnet_create(const agpt_diffnet_cfg* cfg, const float* const* W, int nW, int device);
+void diffnet_set_cond(Handle* h, const float* cond, int B, int T, cudaStream_t st);
+void diffnet_eps(Handle* h, const float* x, const int* t_host, float* eps, cudaStream_t st);
+void gd_p_sample(Handle* h_or_null, const float* x, const float* eps_or_null, const int* t_host, const float* coef_host,
+                 const float* noise, int clip, int B, long n, float* x_out, cudaStream_t st);
+void axpby5(const float* x, const float* e0, const float* e1, const float* e2, const float* e3,
+            const float* coef_host, int B, long n, float* out, cudaStream_t st);
+
+Handle* unet_create(const agpt_unet_cfg* cfg, const float* const* W, int nW, int device);
+void unet_set_context(Handle* h, const float* ctx, int N, int S, cudaStream_t st);
+void unet_forward(Handle* h, const float* x, const int* t_host, int N, int H, int W, float* eps, cudaStream_t st);
+void unet_ddim_sample(Handle* h, const float* x_T, int B, int H, int W, int S, const int* t_steps,
+                      const float* a_t, const float* a_prev, const float* sigma, const float* sqrt_om,
+                      float cfg_scale, float* x_out, cudaStream_t st);
+
 }  // namespace agpt

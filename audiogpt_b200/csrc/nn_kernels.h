@@ -1,0 +1,23 @@
+// Host launchers of the non-contraction kernels (nn_kernels.cu).
+#pragma once
+#include "common.cuh"
+
+namespace agpt {
+
+void groupnorm(const float* x, float* y, const float* gamma, const float* beta, int N, int HW, int C, int G,
+               float eps, bool silu, double* scratch, cudaStream_t st);
+size_t groupnorm_scratch_doubles(int N, int C);
+void layernorm(const float* x, float* y, const float* gamma, const float* beta, long rows, int C, float eps,
+               cudaStream_t st);
+void attention(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch,
+               float* o, int o_pitch, int N, int heads, int d, int Lq, int Lk, cudaStream_t st);
+void timestep_embedding(float* out, const int* t_host, int N, int dim, cudaStream_t st);
+void concat_channels(const float* a, int Ca, const float* b, int Cb, float* out, long rows, cudaStream_t st);
+void upsample_nearest2(const float* in, float* out, int N, int H, int W, int C, cudaStream_t st);
+void im2col_stride2(const float* in, float* col, int N, int H, int W, int C, int Ho, int Wo, cudaStream_t st);
+void cf_to_cl_pad(const float* in, float* out, int N, int C, int Cpad, int HW, cudaStream_t st);
+void ddim_update(const float* x, const float* eps2, int single, float cfg_scale, float a_t, float a_prev,
+                 float sigma_t, float sqrt_om, const float* noise, float temperature, int B, long n,
+                 float* x_prev, float* pred_x0, cudaStream_t st);
+
+}  // namespace agpt

@@ -40,6 +40,12 @@ __device__ __forceinline__ void tc_epilogue(const TapConvParams& P, int g, int p
     case EPI_TANH:
       v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w);
       break;
+    case EPI_MISH:
+      v.x = mishf_(v.x); v.y = mishf_(v.y); v.z = mishf_(v.z); v.w = mishf_(v.w);
+      break;
+    case EPI_SILU:
+      v.x = siluf_(v.x); v.y = siluf_(v.y); v.z = siluf_(v.z); v.w = siluf_(v.w);
+      break;
     case EPI_ADDVEC: {
       const float4 e = *reinterpret_cast<const float4*>(P.evec + (long)g * P.evec_gstride + co);
       v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;

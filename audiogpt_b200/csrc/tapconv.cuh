@@ -38,6 +38,8 @@ enum Epi : int {
   EPI_DIFFOUT = 7,  // co<csplit: out=(out+v)*rsqrt2 in place ; else out2 (+)= v
   EPI_STORE_CF = 8, // channels-first store out[g][co][p]
   EPI_TANH = 9,     // tanh(v + bias)
+  EPI_MISH = 10,    // mish(v + bias) = x * tanh(softplus(x))   (NeuralSeq/modules/diff/diffusion.py:68-70)
+  EPI_SILU = 11,    // silu(v + bias)
 };
 
 struct TapConvParams {

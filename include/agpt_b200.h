@@ -87,13 +87,15 @@ int agpt_diffnet_create(const agpt_diffnet_cfg* cfg, const float* const* host_we
 int agpt_diffnet_set_cond(agpt_handle h, const float* cond, int B, int T, void* stream);
 /* eps [B,1,M,T] = DiffNet(x [B,1,M,T], t [B] (host ints), cond set above)    */
 int agpt_diffnet_eps(agpt_handle h, const float* x, const int* t_host, float* eps, void* stream);
-/* x_out = p_sample(x, t, noise) with eps computed internally; coef[b] =
- * {sqrt_recip_ac, sqrt_recipm1_ac, post_mean_coef1, post_mean_coef2,
- *  exp(0.5*post_log_var) * (t!=0)} gathered on the host from the fp32 tables
- * (shallow_diffusion_tts.py:108-123).  clip: clamp x0 to [-1,1] (:153-154).
- * x_out may alias x.                                                         */
-int agpt_gd_p_sample(agpt_handle h, const float* x, const int* t_host, const float* coef_host /*[B][5]*/,
-                     const float* noise, int clip_denoised, float* x_out, void* stream);
+/* x_out = p_sample(x, t, noise): eps is taken from `eps` when non-NULL (any
+ * denoise_fn), else computed by the DiffNet handle `h` (cond set above).
+ * coef_host[b] = {sqrt_recip_ac[t], sqrt_recipm1_ac[t], post_mean_coef1[t],
+ * post_mean_coef2[t], exp(0.5*post_log_var[t]) * (t!=0)} gathered on the host
+ * from the fp32 tables (shallow_diffusion_tts.py:108-123,159-166).  clip: clamp
+ * x0 to [-1,1] (:153-154).  n_per_sample = M*T.  x_out may alias x.           */
+int agpt_gd_p_sample(agpt_handle h_or_null, const float* x, const float* eps_or_null, const int* t_host,
+                     const float* coef_host /*[B][5]*/, const float* noise_or_null, int clip_denoised,
+                     int B, long n_per_sample, float* x_out, void* stream);
 /* generic elementwise: out = a0*x + a1*e0 + a2*e1 + a3*e2 + a4*e3 (per-sample
  * coefficient rows coef_host[B][5]; NULL e_i are skipped) -- the PLMS
  * combinations of shallow_diffusion_tts.py:174-204.                          */
