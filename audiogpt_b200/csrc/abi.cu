@@ -2,6 +2,7 @@
 #include <atomic>
 #include "models.h"
 #include "nn_kernels.h"
+#include "tapconv.cuh"
 
 namespace agpt {
 static thread_local std::string g_last_error;
@@ -37,6 +38,16 @@ extern "C" {
 const char* agpt_last_error(void) { return g_last_error.c_str(); }
 int agpt_version(void) { return 100; }
 long long agpt_launch_count(void) { return g_launches.load(); }
+
+int agpt_profile_enable(int on) { return guarded([&] { profile_enable(on); }); }
+int agpt_profile_collect(double ms[3], double flops[3], double bytes[3], long long launches[3]) {
+  return guarded([&] { profile_collect(ms, flops, bytes, launches); });
+}
+double agpt_fma_peak_tflops(void) {
+  double v = -1.0;
+  guarded([&] { v = fma_peak_tflops(); });
+  return v;
+}
 
 void agpt_destroy(agpt_handle h) {
   auto* p = reinterpret_cast<Handle*>(h);

@@ -4,6 +4,70 @@
 
 namespace agpt {
 
+// ---- optional per-launch CUDA-event profiling (bench.py's roofline leg) ----
+struct ProfRec { cudaEvent_t e0, e1; int variant; double flops, bytes; };
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs;
+
+void profile_enable(int on) {
+  g_prof = on != 0;
+  if (!on) {
+    for (auto& r : g_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_recs.clear();
+  }
+}
+
+// Sums over the records since profile_enable(1): per tile variant (BN = 128, 64, 32)
+void profile_collect(double* ms, double* flops, double* bytes, long long* launches) {
+  for (int v = 0; v < 3; ++v) { ms[v] = 0; flops[v] = 0; bytes[v] = 0; launches[v] = 0; }
+  AGPT_CUDA(cudaDeviceSynchronize());
+  for (auto& r : g_recs) {
+    float t = 0.f;
+    AGPT_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms[r.variant] += t; flops[r.variant] += r.flops; bytes[r.variant] += r.bytes; launches[r.variant] += 1;
+  }
+}
+
+// ---- fp32 FMA saturation probe: the measured denominator of the compute roofline ----
+__global__ void fma_peak_kernel(float* out, int iters) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = (float)(threadIdx.x + i) * 1e-3f;
+  const float b = 1.000001f, c = 1e-6f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], b, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == 12345.678f) out[0] = s;
+}
+
+double fma_peak_tflops() {
+  float* d = nullptr;
+  AGPT_CUDA(cudaMalloc(&d, 4));
+  int dev = 0, sms = 0;
+  AGPT_CUDA(cudaGetDevice(&dev));
+  AGPT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int iters = 1 << 15, blocks = sms * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  AGPT_CUDA(cudaEventCreate(&e0)); AGPT_CUDA(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    AGPT_CUDA(cudaEventRecord(e0));
+    fma_peak_kernel<<<blocks, threads>>>(d, iters);
+    AGPT_CUDA(cudaEventRecord(e1));
+    AGPT_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    AGPT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * iters * (double)blocks * threads;
+    best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  return best;
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
@@ -237,7 +301,10 @@ void tapconv_launch(TapConvParams P, cudaStream_t st) {
   const int bn = tc_pick_bn(P.Cout);
   const size_t smem = ((size_t)(R + 8) + 4 * TC_KC * (size_t)R + 2 * TC_KC * (size_t)bn) * sizeof(float);
   dim3 grid(cdiv(Lv, TC_BM), cdiv(P.Cout, bn), P.G);
-  static bool attr_done = false;
+  int dev = 0;
+  AGPT_CUDA(cudaGetDevice(&dev));
+  static bool attr_done_dev[64] = {false};
+  bool& attr_done = attr_done_dev[dev & 63];
   if (!attr_done) {
     AGPT_CUDA(cudaFuncSetAttribute(tapconv_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     AGPT_CUDA(cudaFuncSetAttribute(tapconv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -245,9 +312,25 @@ void tapconv_launch(TapConvParams P, cudaStream_t st) {
     attr_done = true;
   }
   AGPT_CHECK(smem <= 100 * 1024, "tapconv smem too large (image too wide?)");
+  ProfRec* rec = nullptr;
+  if (g_prof) {
+    g_recs.emplace_back();
+    rec = &g_recs.back();
+    rec->variant = bn == 128 ? 0 : (bn == 64 ? 1 : 2);
+    const double rows = (double)P.G * P.L;
+    rec->flops = 2.0 * rows * P.Cin * P.Cout * P.ntaps * (P.flops_scale > 0.f ? P.flops_scale : 1.f);
+    const int out_c = (P.epi == EPI_GATE || P.epi == EPI_GEGLU) ? P.Cout / 2 : P.Cout;
+    rec->bytes = 4.0 * (rows * P.Cin + rows * out_c + (P.res ? rows * P.Cout : 0.0) +
+                        (P.epi == EPI_ACC && P.accumulate ? rows * P.Cout : 0.0) +
+                        (double)P.ntaps * P.Cin * P.Cout);
+    AGPT_CUDA(cudaEventCreate(&rec->e0));
+    AGPT_CUDA(cudaEventCreate(&rec->e1));
+    AGPT_CUDA(cudaEventRecord(rec->e0, st));
+  }
   if (bn == 128) tapconv_kernel<128><<<grid, 256, smem, st>>>(P);
   else if (bn == 64) tapconv_kernel<64><<<grid, 128, smem, st>>>(P);
   else tapconv_kernel<32><<<grid, 64, smem, st>>>(P);
+  if (rec) AGPT_CUDA(cudaEventRecord(rec->e1, st));
   count_launch(1);
   AGPT_CUDA(cudaGetLastError());
 }

@@ -54,6 +54,7 @@ struct TapConvParams {
   int epi; const float* res; long res_gstride; int res_pitch; float scale; int accumulate;
   const float* evec; int evec_gstride;
   float* out2; long out2_gstride; int out2_pitch; int csplit;
+  float flops_scale;   // useful fraction of the MACs (zero-padded polyphase taps); 0 => 1
 };
 
 // ---------------------------------------------------------------- host side
@@ -63,6 +64,7 @@ struct PackedConv {
   int tap_off_1d[kMaxTaps] = {0};   // for 1-D convs: row offsets; 2-D convs derive offsets from W at launch
   bool is2d = false;
   bool has_bias = false;
+  float useful = 1.f;   // fraction of packed taps that are algorithmic work
 };
 
 inline int tc_pick_bn(int cout) {
@@ -74,6 +76,9 @@ inline int tc_pick_bn(int cout) {
 
 // Fill geometry-dependent fields (offsets, halo, smem rows) and launch (tapconv.cu).
 void tapconv_launch(TapConvParams P, cudaStream_t st);
+void profile_enable(int on);
+void profile_collect(double* ms, double* flops, double* bytes, long long* launches);
+double fma_peak_tflops();
 
 // Common setup from a PackedConv; caller fills in/out/pro/epi afterwards.
 inline TapConvParams tapconv_params(const PackedConv& pc, int G, int L, int Wreal, int dil) {
@@ -93,6 +98,7 @@ inline TapConvParams tapconv_params(const PackedConv& pc, int G, int L, int Wrea
     for (int t = 0; t < pc.ntaps; ++t) P.tap_off[t] = pc.tap_off_1d[t] * dil;
   }
   P.scale = 1.f;
+  P.flops_scale = pc.useful;
   return P;
 }
 
@@ -158,6 +164,7 @@ inline void pack_convtranspose(PackedConv& pc, const float* w, const float* b, i
     }
   }
   pc.w.upload(h);
+  pc.useful = (float)(K / (double)u) / (float)pc.ntaps;
   pc.has_bias = b != nullptr;
   std::vector<float> hb(pc.cout_pad, 0.f);
   if (b) for (int r = 0; r < u; ++r) for (int co = 0; co < Cout; ++co) hb[r * Cout + co] = b[co];

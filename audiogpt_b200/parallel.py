@@ -1,0 +1,113 @@
+"""Batch sharding of independent utterances / clips over the GPUs of one box.
+
+The hot path has no cross-sample operation (GroupNorm/LayerNorm/attention are per sample,
+CFG pairs stay on one GPU), so the data path shards with NO collective.
+The only collectives are the two the north star names, both outside the kernels:
+
+* one broadcast of the packed weights at start-up (``broadcast_state_dict``), and
+* one all-gather of the finished fp32 waveforms per batch (``all_gather_rows``).
+
+One process per GPU (``torch.distributed``; NCCL over NVLink on the B200 box, gloo in the
+CPU tests).  The reference has no inference-time multi-GPU at all: its tool classes are
+pinned to fixed devices by hand (audio-chatgpt.py:1051-1073).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(backend: str = None) -> Tuple[int, int, int]:
+    """(rank, world, local_rank) from the torchrun environment; no-op when WORLD_SIZE is unset/1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_range(total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous ceil(total/world) slices; trailing ranks may get fewer (or zero) items."""
+    per = -(-total // world)
+    lo = min(total, rank * per)
+    return lo, min(total, lo + per)
+
+
+def broadcast_state_dict(sd: Dict[str, torch.Tensor], src: int = 0, device=None) -> Dict[str, torch.Tensor]:
+    """One flat fp32 blob, one broadcast.  Every rank passes a dict with the same keys/shapes
+    (contents only matter on ``src``)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return sd
+    keys = list(sd.keys())
+    sizes = [sd[k].numel() for k in keys]
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                             if dist.get_backend() == "nccl" else torch.device("cpu"))
+    flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+    if dist.get_rank() == src:
+        off = 0
+        for k, n in zip(keys, sizes):
+            flat[off:off + n].copy_(sd[k].reshape(-1))
+            off += n
+    dist.broadcast(flat, src=src)
+    out, off = {}, 0
+    flat_cpu = flat.cpu()
+    for k, n in zip(keys, sizes):
+        out[k] = flat_cpu[off:off + n].reshape(sd[k].shape).clone()
+        off += n
+    return out
+
+
+def all_gather_rows(x: torch.Tensor, counts: Sequence[int] = None) -> torch.Tensor:
+    """Concatenate per-rank row blocks [b_r, ...] along dim 0 on every rank.  ``counts`` (rows
+    per rank) enables ragged shards; blocks are padded to max(counts) for the collective."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return x
+    world = dist.get_world_size()
+    if counts is None:
+        out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x.contiguous())
+        return out
+    m = max(counts)
+    pad = torch.zeros((m,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    pad[: x.shape[0]] = x
+    out = torch.empty((world * m,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, pad)
+    return torch.cat([out[r * m: r * m + counts[r]] for r in range(world)], dim=0)
+
+
+# ---- mixed dispatch (BASELINE configs[4]): greedy longest-processing-time assignment ----
+HIFIGAN_GFLOP_PER_FRAME = 0.614          # V1, SURVEY.md 8d
+DDIM100_TFLOP_PER_CLIP = 18.66 + 0.39    # UNet x200 forwards + VAE decode
+
+
+def job_cost_tflop(kind: str, frames: int = 0) -> float:
+    if kind == "tts":
+        return HIFIGAN_GFLOP_PER_FRAME * frames * 1e-3
+    if kind == "t2a":
+        return DDIM100_TFLOP_PER_CLIP + HIFIGAN_GFLOP_PER_FRAME * 624 * 1e-3
+    raise ValueError(kind)
+
+
+def lpt_assign(costs: Sequence[float], workers: int) -> List[List[int]]:
+    """Greedy LPT: jobs sorted by decreasing cost, each to the currently least-loaded worker.
+    Returns per-worker job-index lists (deterministic: ties broken by lower worker id)."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    load = [0.0] * workers
+    out: List[List[int]] = [[] for _ in range(workers)]
+    for i in order:
+        w = min(range(workers), key=lambda j: (load[j], j))
+        out[w].append(i)
+        load[w] += costs[i]
+    return out

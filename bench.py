@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the AudioGPT generative hot path on B200 (contract: see the task brief).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Headline workload (BASELINE.json configs[1], the configuration the metric is quoted on that
+fits one GPU): HiFi-GAN V1 (22.05 kHz, hop 256) vocoding a batch of 8 synthetic 80-bin mels of
+800 frames each -- what `FastSpeech2 TTS -> HiFi-GAN, batch 8` hands to the vocoder.  A step is
+one pass of that batch through `HifiGanGenerator.forward`.  Weights are seeded random of the
+V1 architecture (no checkpoints offline).  Metric: mel-frames/s vocoded (whole job).
+
+  value     : device-resident inputs, CUDA-event timed, barrier + synchronize on both sides
+  e2e       : the same metric through the host-buffer C-ABI call
+              (agpt_hifigan_vocode_host: pinned H2D of the mel, forward, D2H of the waveform)
+  roofline  : dominant kernel (tapconv) -- fp32-FMA bound; achieved = algorithmic FLOPs /
+              CUDA-event launch durations measured live; peak = FMA saturation probe run here
+              (the HBM view, as BASELINE asks, is reported beside it against MEASURED_PEAKS.json)
+  cpu_baseline / --impl reference : the CPU oracle (oracle/hifigan_ref.py, a restatement of the
+              reference's forward on torch's own fp32 CPU kernels) on the host cores
+  extra     : clips/s for Make-An-Audio DDIM-100 (C4 per-GPU shard) and utterances/s for the
+              DiffSinger 100-step p_sample chain (C3), each one full un-shortened run
+
+With N > 1 (torchrun, one rank per GPU) every rank vocodes its own batch of 8 (weak scaling,
+no data-path collective); weights are broadcast once from rank 0 and the finished waveforms
+are all-gathered inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+B_PER_GPU, T_FRAMES, HOP, SR = 8, 800, 256, 22050
+METRIC, UNIT = "mel_frames_per_s_vocoded", "frames/s"
+WORKLOAD = "HiFi-GAN V1 22.05kHz vocoder, batch 8 x 800 mel frames per GPU (FastSpeech2->HiFi-GAN, BASELINE configs[1])"
+
+
+def base_config(n_gpus):
+    return {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "frames_per_utt": T_FRAMES,
+            "global_batch": B_PER_GPU * n_gpus, "hop": HOP, "sample_rate": SR,
+            "weights": "seeded random (specs.synth_hifigan(HIFIGAN_V1, 1234))",
+            "parallelism": f"batch-sharded x{n_gpus}, no data-path collective",
+            "l2_policy": "activation working set per step ~2.5 GB >> 126 MB L2 (no explicit flush needed)"}
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(self.gpu), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            hi = [v for v in sm if v >= 0.5 * max(sm)]   # samples under load
+            out = {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_vocode_rate(steps, warmup, batch, frames):
+    """frames/s of the CPU oracle (the reference's forward restated on torch fp32 CPU ops)."""
+    from audiogpt_b200 import specs
+    from oracle import hifigan_ref as hr
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    h = specs.HIFIGAN_V1
+    sd = specs.synth_hifigan(h, 1234)
+    mel = specs.synth_tensor((batch, 80, frames), seed=0, scale=2.0, shift=-4.0)
+    for _ in range(warmup):
+        hr.hifigan_forward(sd, h, mel)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        hr.hifigan_forward(sd, h, mel)
+        ts.append(time.perf_counter() - t0)
+    sec = sum(ts) / len(ts)
+    return batch * frames / sec, sec, cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample of the same workload: 2 of the 8 utterances per step (same T), scaled linearly
+    sb = 2
+    rate, sec, cores = cpu_vocode_rate(args.steps, max(1, min(args.warmup, 2)), sb, T_FRAMES)
+    sample = f"{sb} of {B_PER_GPU} utterances x {T_FRAMES} frames per step, {args.steps} steps, {cores} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * (B_PER_GPU / sb),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": base_config(args.gpus),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "CPU oracle port of HifiGanGenerator.forward (the reference is pure PyTorch; /root/reference "
+                    "does not travel to the GPU box); RTF = value*hop/sample_rate"}
+    line["x_realtime"] = rate * HOP / SR
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    from audiogpt_b200 import _lib, parallel, specs
+    from audiogpt_b200.modules.hifigan.hifigan import HifiGanGenerator
+
+    rank, world, local = parallel.init_distributed()
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    n_gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    L = _lib.lib()
+    L.agpt_fma_peak_tflops.restype = __import__("ctypes").c_double
+
+    h = specs.HIFIGAN_V1
+    shapes = specs.hifigan_param_shapes(h)
+    sd = specs.synth_hifigan(h, 1234) if rank == 0 else {k: torch.empty(s) for k, s in shapes.items()}
+    sd = parallel.broadcast_state_dict(sd, src=0)          # the one weight broadcast (NCCL over NVLink)
+    model = HifiGanGenerator(h)
+    model.load_state_dict(sd, strict=True)
+    model = model.eval().to(dev)
+    mel_host = specs.synth_tensor((B_PER_GPU, 80, T_FRAMES), seed=100 + rank, scale=2.0, shift=-4.0)
+    mel = mel_host.to(dev)
+    frames_step = B_PER_GPU * T_FRAMES * n_gpus
+
+    def barrier():
+        if n_gpus > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_device():
+        wav = model(mel)
+        if n_gpus > 1:
+            wav = parallel.all_gather_rows(wav)             # finished waveforms gathered on every rank
+        return wav
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - l0
+    if n_gpus > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = frames_step / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers through the C-ABI (H2D + forward + D2H + sync inside the call)
+    mel_np = mel_host.numpy()
+    for _ in range(max(1, args.warmup // 2)):
+        model.vocode_host(mel_np, device=dev)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        wav_np = model.vocode_host(mel_np, device=dev)
+    barrier()
+    e2e_sec = (time.perf_counter() - t0) / args.steps
+    if n_gpus > 1:
+        tt = torch.tensor([e2e_sec], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_sec = float(tt.item())
+    e2e = {"value": frames_step / e2e_sec, "unit": UNIT,
+           "h2d_bytes_per_step": int(mel_np.nbytes), "d2h_bytes_per_step": int(wav_np.nbytes),
+           "api": "HifiGanGenerator.vocode_host -> agpt_hifigan_vocode_host (numpy in / numpy out)"}
+
+    if rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel, measured live with CUDA events around every launch
+    import ctypes as C
+    fma_peak = float(L.agpt_fma_peak_tflops())
+    _lib.check(L.agpt_profile_enable(1))
+    model(mel)
+    msv, flv, byv, lnv = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_double * 3)(), (C.c_longlong * 3)()
+    _lib.check(L.agpt_profile_collect(msv, flv, byv, lnv))
+    _lib.check(L.agpt_profile_enable(0))
+    tot_ms = sum(msv)
+    ach_tf = sum(flv) / (tot_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "tapconv_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    variants = ["BN128", "BN64", "BN32"]
+    roofline = {
+        "kernel": "tapconv_kernel<BN> (all contractions of the generator; share of step below)",
+        "bound": "fma_fp32",
+        "achieved": ach_tf, "peak": fma_peak, "unit": "TFLOP/s", "frac": ach_tf / fma_peak if fma_peak > 0 else None,
+        "peak_source": "fp32 FFMA saturation probe run in this process (agpt_fma_peak_tflops); "
+                       "MEASURED_PEAKS.json has no fp32-FMA entry",
+        "share_of_step": tot_ms / ms_per_step if n_gpus == 1 else None,
+        "per_variant": {variants[i]: {"launches": int(lnv[i]), "ms": msv[i],
+                                      "tflops": (flv[i] / (msv[i] * 1e-3) / 1e12) if msv[i] > 0 else None,
+                                      "gbs": (byv[i] / (msv[i] * 1e-3) / 1e9) if msv[i] > 0 else None}
+                        for i in range(3)},
+        "hbm": {"bound": "hbm", "achieved": sum(byv) / (tot_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": sum(byv) / (tot_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
+                "note": "algorithmic bytes (in+out+residual+weights per launch); the path is compute-bound "
+                        "(AI ~ 10^3 FLOP/B, SURVEY.md 8d) so this fraction is small by construction"},
+        "traffic": traffic,
+    }
+
+    # ---- CPU baseline on this box's host cores (bounded sample)
+    cb_rate, cb_sec, cores = cpu_vocode_rate(3, 1, 2, T_FRAMES)
+    cpu_baseline = {"value": cb_rate, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"2 of {B_PER_GPU} utterances x {T_FRAMES} frames, 1 warm-up + 3 timed passes of "
+                              f"oracle/hifigan_ref.py on {cores} threads"}
+
+    extra = {}
+    if not args.no_extra:
+        try:
+            extra = extra_metrics(dev)
+        except Exception as ex:  # extras must never take the headline down
+            extra = {"error": repr(ex)}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": base_config(n_gpus),
+            "x_realtime": value * HOP / SR, "x_realtime_per_gpu": value * HOP / SR / n_gpus,
+            "tflops_fp32": 0.614e9 * value / 1e12,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "extra": extra}
+    print(json.dumps(line))
+
+
+def extra_metrics(dev):
+    """Secondary BASELINE metrics, each one complete run: DDIM-100+CFG clips/s on the C4 per-GPU shard
+    (4 clips -> CFG batch 8 on the 4x10x78 latent) and the C3 DiffSinger chain (16 utt x 400 frames,
+    100 ancestral p_sample steps) -> utterances/s."""
+    from audiogpt_b200 import specs
+    from audiogpt_b200.ldm.models.diffusion.ddim import DDIMSampler, LatentDiffusionShim
+    from audiogpt_b200.ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from audiogpt_b200.modules.diff import shallow_diffusion_tts as sdt
+    from audiogpt_b200.modules.diff.net import DiffNet
+    from audiogpt_b200.utils.hparams import set_hparams_from_dict
+    out = {}
+    # --- C4 shard
+    cfg = specs.UNET_TXT2AUDIO
+    u = UNetModel(image_size=32, use_checkpoint=True, **cfg)
+    u.load_state_dict(specs.synth_unet(cfg, 4040), strict=True)
+    u = u.eval().to(dev)
+    ldm = LatentDiffusionShim(u).to(dev)
+    smp = DDIMSampler(ldm)
+    B = 4
+    xT = torch.tensor(np.random.RandomState(55).randn(B, 4, 10, 78), dtype=torch.float32, device=dev)
+    c = specs.synth_tensor((B, 77, 1024), seed=5).to(dev)
+    uc = specs.synth_tensor((1, 77, 1024), seed=6).expand(B, -1, -1).contiguous().to(dev)
+    smp.sample(S=4, batch_size=B, shape=(4, 10, 78), conditioning=c, verbose=False, x_T=xT,
+               unconditional_guidance_scale=1.5, unconditional_conditioning=uc)          # warm-up
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    z, _ = smp.sample(S=100, batch_size=B, shape=(4, 10, 78), conditioning=c, verbose=False, x_T=xT,
+                      unconditional_guidance_scale=1.5, unconditional_conditioning=uc)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    out["ddim100_cfg1.5_clips_per_s_per_gpu"] = B / dt
+    out["ddim100_seconds_for_4_clips"] = dt
+    out["ddim100_unet_tflops"] = 18.66 * B / dt
+    del u, ldm, smp
+    torch.cuda.empty_cache()
+    # --- C3
+    cfgd = specs.DIFFNET_BASE
+    set_hparams_from_dict(dict(cfgd, keep_bins=80, schedule_type="linear", max_beta=0.06))
+    net = DiffNet(80)
+    net.load_state_dict(specs.synth_diffnet(cfgd, 2025), strict=True)
+    gd = sdt.GaussianDiffusion(None, 80, net, timesteps=100, K_step=100, loss_type="l1",
+                               betas=sdt.linear_beta_schedule(100, 0.06), spec_min=specs.SPEC_MIN,
+                               spec_max=specs.SPEC_MAX).eval().to(dev)
+    Bc, Tc = 16, 400
+    x = specs.synth_tensor((Bc, 1, 80, Tc), seed=2).to(dev)
+    cond = specs.synth_tensor((Bc, 256, Tc), seed=3).to(dev)
+    gd.sample(cond, x_start=x, t_start=3)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    gd.sample(cond, x_start=x)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    out["diffsinger_c3_utt_per_s"] = Bc / dt
+    out["diffsinger_c3_seconds_16utt_100steps"] = dt
+    out["diffsinger_c3_tflops"] = 26.44e6 * Bc * Tc * 100 / dt / 1e12
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary DDIM / DiffSinger measurements")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (audiogpt_b200 has no CPU fallback)")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,12 @@ int agpt_version(void);
 /* number of kernels launched by this library in this process so far (bench.py's gpu_launches) */
 long long agpt_launch_count(void);
 void agpt_destroy(agpt_handle h);
+/* Measurement helpers (bench.py): per-launch CUDA-event timing of the tapconv kernel,
+ * summed per tile variant v = {0: BN=128, 1: BN=64, 2: BN=32}; and an fp32-FMA
+ * saturation probe returning the measured TFLOP/s of the current device.       */
+int agpt_profile_enable(int on);
+int agpt_profile_collect(double ms[3], double flops[3], double bytes[3], long long launches[3]);
+double agpt_fma_peak_tflops(void);
 
 /* ------------------------------------------------------------------ HiFi-GAN
  * Replaces HifiGanGenerator.__init__/forward/remove_weight_norm

@@ -1,0 +1,180 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, host-side logic
+(state-dict layouts, weight-norm folding, schedules, sharding / LPT) and the world_size-2
+gloo path of audiogpt_b200.parallel.  No compute calls into the CUDA library here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from audiogpt_b200 import parallel, specs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from audiogpt_b200.build import build
+    lib_path = build()
+    hdr = open(os.path.join(ROOT, "include", "agpt_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(agpt_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 18
+    L = ctypes.CDLL(lib_path)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/agpt_b200.h but not exported"
+    L.agpt_last_error.restype = ctypes.c_char_p
+    assert L.agpt_version() >= 100
+    assert isinstance(L.agpt_last_error(), bytes)
+
+
+def test_invalid_handle_is_an_error_not_a_crash():
+    from audiogpt_b200 import _lib
+    L = _lib.lib()
+    rc = L.agpt_diffnet_set_cond(None, None, 1, 1, None)
+    assert rc != 0 and b"invalid handle" in L.agpt_last_error()
+
+
+def test_no_cpu_fallback():
+    from audiogpt_b200.modules.hifigan.hifigan import HifiGanGenerator
+    m = HifiGanGenerator(specs.HIFIGAN_SMALL)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m(torch.zeros(1, 80, 4))
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for dp, _, fs in os.walk(os.path.join(ROOT, "audiogpt_b200")):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M):
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_param_tables_match_survey_counts():
+    n = lambda shapes: sum(int(np.prod(s)) for s in shapes.values())
+    assert n(specs.hifigan_param_shapes(specs.HIFIGAN_V1)) == 13_926_017   # 13.93 M
+    assert abs(n(specs.diffnet_param_shapes(specs.DIFFNET_BASE)) / 15.09e6 - 1) < 0.01
+    assert abs(n(specs.unet_param_shapes(specs.UNET_TXT2AUDIO)) / 160.2e6 - 1) < 0.01
+    plan = specs.unet_plan(specs.UNET_TXT2AUDIO)
+    assert len(plan["input_blocks"]) == 6 and len(plan["output_blocks"]) == 6
+    kinds = [[l[0] for l in b] for b in plan["output_blocks"]]
+    assert kinds[2] == ["res", "st", "up"] and plan["output_blocks"][0][0][1:3] == (1280, 640)
+    assert plan["output_blocks"][2][0][1:3] == (960, 640) and plan["output_blocks"][3][0][1:3] == (960, 320)
+
+
+def test_weight_norm_fold_matches_torch():
+    from audiogpt_b200.modules.hifigan.hifigan import fold_weight_norm
+    g = torch.Generator().manual_seed(0)
+    for shape in [(8, 4, 3), (6, 5, 16)]:      # Conv1d [Cout,Cin,k] and ConvTranspose1d [Cin,Cout,k]
+        v = torch.randn(shape, generator=g)
+        gg = torch.rand((shape[0], 1, 1), generator=g) + 0.5
+        ref = torch._weight_norm(v, gg, 0)
+        assert torch.allclose(fold_weight_norm(gg, v), ref, atol=1e-6)
+
+
+def test_hifigan_state_dict_roundtrip_both_layouts():
+    from audiogpt_b200.modules.hifigan.hifigan import HifiGanGenerator
+    h = specs.HIFIGAN_SMALL
+    m = HifiGanGenerator(h)
+    sd_wn = m.state_dict()
+    assert any(k.endswith("weight_g") for k in sd_wn)
+    m2 = HifiGanGenerator(h)
+    m2.load_state_dict(sd_wn, strict=True)
+    m2.remove_weight_norm()
+    assert list(m2.state_dict().keys()).count("conv_pre.weight") == 1
+    m3 = HifiGanGenerator(h)                       # folded checkpoint into a fresh (weight-normed) module
+    m3.load_state_dict(m2.state_dict(), strict=True)
+    for a, b in zip(m2.folded_weights(), m3.folded_weights()):
+        assert torch.equal(a, b)
+    m4 = HifiGanGenerator(h)
+    m4.remove_weight_norm()                        # g/v checkpoint into an already-folded module
+    m4.load_state_dict(sd_wn, strict=True)
+    for a, b in zip(m2.folded_weights(), m4.folded_weights()):
+        assert torch.allclose(a, b, atol=1e-7)
+
+
+def test_gaussian_diffusion_buffers_and_plms_scalars():
+    from audiogpt_b200.modules.diff import shallow_diffusion_tts as sdt
+    from audiogpt_b200.utils.hparams import set_hparams_from_dict
+    from oracle import diffusion_ref as dr
+    set_hparams_from_dict(dict(specs.DIFFNET_SMALL, keep_bins=80, schedule_type="linear", max_beta=0.06))
+    gd = sdt.GaussianDiffusion(None, 80, torch.nn.Identity(), timesteps=100, K_step=100,
+                               spec_min=specs.SPEC_MIN, spec_max=specs.SPEC_MAX)
+    tab = dr.schedule_tables(dr.linear_betas(100, 0.06))
+    for k, v in tab.items():
+        assert torch.equal(getattr(gd, k), v), k
+    # fused PLMS scalars reproduce get_x_pred
+    x, e = torch.randn(1, 1, 80, 5), torch.randn(1, 1, 80, 5)
+    for tv in (99, 50, 7):
+        a, b = gd._plms_scalars(tv, 10)
+        ref = dr.plms_x_pred(tab, x, e, torch.tensor([tv]), 10)
+        assert torch.allclose(a * x + b * e, ref, atol=1e-5)
+
+
+def test_ddim_tables_match_oracle():
+    from audiogpt_b200.ldm.models.diffusion.ddim import DDIMSampler, LatentDiffusionShim
+    from oracle import ldm_ref as lr
+    ldm = LatentDiffusionShim(torch.nn.Identity())
+    s = DDIMSampler(ldm)
+    s.make_schedule(100, ddim_eta=0.0, verbose=False)
+    tab = lr.ddim_tables(lr.ldm_schedule()["alphas_cumprod"], 100)
+    assert np.array_equal(s.ddim_timesteps, tab["timesteps"]) and s.ddim_timesteps[0] == 1 and s.ddim_timesteps[-1] == 991
+    assert torch.equal(s.ddim_alphas, torch.as_tensor(tab["alphas"]))
+    assert np.array_equal(s.ddim_alphas_prev.double().numpy(), np.asarray(tab["alphas_prev"], dtype=np.float64))
+
+
+def test_shard_range_and_lpt():
+    assert [parallel.shard_range(32, 8, r) for r in range(8)] == [(4 * r, 4 * r + 4) for r in range(8)]
+    assert [parallel.shard_range(10, 4, r) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert parallel.shard_range(2, 4, 3) == (2, 2)
+    rng = np.random.RandomState(7)
+    costs = [parallel.job_cost_tflop("tts", int(t)) for t in rng.randint(200, 801, 32)] + \
+            [parallel.job_cost_tflop("t2a")] * 32
+    asg = parallel.lpt_assign(costs, 8)
+    assert sorted(i for w in asg for i in w) == list(range(64))
+    loads = [sum(costs[i] for i in w) for w in asg]
+    assert max(loads) / (sum(costs) / 8) < 1.05          # 32 equal big jobs over 8 GPUs + small fill
+    assert all(sum(1 for i in w if i >= 32) == 4 for w in asg)
+
+
+WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, {root!r})
+from audiogpt_b200 import parallel, specs
+rank, world, local = parallel.init_distributed("gloo")
+assert world == 2
+h = specs.HIFIGAN_SMALL
+shapes = specs.hifigan_param_shapes(h)
+sd = specs.synth_hifigan(h, 1234) if rank == 0 else {{k: torch.zeros(s) for k, s in shapes.items()}}
+sd = parallel.broadcast_state_dict(sd, src=0)
+ref = specs.synth_hifigan(h, 1234)
+assert all(torch.equal(sd[k], ref[k]) for k in ref), "broadcast mismatch"
+lo, hi = parallel.shard_range(5, world, rank)          # ragged: 3 + 2 utterances
+mine = torch.arange(lo, hi, dtype=torch.float32)[:, None, None].expand(hi - lo, 1, 7).contiguous()
+allw = parallel.all_gather_rows(mine, counts=[3, 2])
+assert allw.shape == (5, 1, 7) and torch.equal(allw[:, 0, 0], torch.arange(5.0))
+eq = parallel.all_gather_rows(torch.full((2, 3), float(rank)))
+assert eq.shape == (4, 3) and eq[0, 0] == 0 and eq[3, 0] == 1
+print("rank", rank, "ok")
+"""
+
+
+def test_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2", CUDA_VISIBLE_DEVICES="")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"rank {r} ok" in o
