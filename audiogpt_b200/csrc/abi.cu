@@ -40,9 +40,10 @@ int agpt_version(void) { return 100; }
 long long agpt_launch_count(void) { return g_launches.load(); }
 
 int agpt_profile_enable(int on) { return guarded([&] { profile_enable(on); }); }
-int agpt_profile_collect(double ms[3], double flops[3], double bytes[3], long long launches[3]) {
+int agpt_profile_collect(double ms[4], double flops[4], double bytes[4], long long launches[4]) {
   return guarded([&] { profile_collect(ms, flops, bytes, launches); });
 }
+int agpt_set_tensor_cores(int on) { return guarded([&] { tc_set_enabled(on); }); }
 double agpt_fma_peak_tflops(void) {
   double v = -1.0;
   guarded([&] { v = fma_peak_tflops(); });

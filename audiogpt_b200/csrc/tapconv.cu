@@ -1,5 +1,6 @@
 // tapconv kernel (fp32 FMA) + launcher.  See tapconv.cuh for the contract.
 #include "tapconv.cuh"
+#include "tapconv_epi.cuh"
 #include "models.h"
 
 namespace agpt {
@@ -17,9 +18,9 @@ void profile_enable(int on) {
   }
 }
 
-// Sums over the records since profile_enable(1): per tile variant (BN = 128, 64, 32)
+// Sums over the records since profile_enable(1): per variant (FMA BN = 128, 64, 32; 3 = tcgen05)
 void profile_collect(double* ms, double* flops, double* bytes, long long* launches) {
-  for (int v = 0; v < 3; ++v) { ms[v] = 0; flops[v] = 0; bytes[v] = 0; launches[v] = 0; }
+  for (int v = 0; v < 4; ++v) { ms[v] = 0; flops[v] = 0; bytes[v] = 0; launches[v] = 0; }
   AGPT_CUDA(cudaDeviceSynchronize());
   for (auto& r : g_recs) {
     float t = 0.f;
@@ -74,93 +75,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
-
-__device__ __forceinline__ void tc_epilogue(const TapConvParams& P, int g, int p, int co, float4 v) {
-  if (co >= P.Cout) return;
-  if (P.bias) {
-    const float4 b = *reinterpret_cast<const float4*>(P.bias + co);
-    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-  }
-  switch (P.epi) {
-    case EPI_BIAS: break;
-    case EPI_RES:
-    case EPI_ACC: {
-      if (P.res) {
-        const float4 r = *reinterpret_cast<const float4*>(P.res + g * P.res_gstride + (long)p * P.res_pitch + co);
-        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-      }
-      if (P.epi == EPI_ACC) {
-        v.x *= P.scale; v.y *= P.scale; v.z *= P.scale; v.w *= P.scale;
-        if (P.accumulate) {
-          const float4 o = *reinterpret_cast<const float4*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + co);
-          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-        }
-      }
-      break;
-    }
-    case EPI_RELU:
-      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-      break;
-    case EPI_TANH:
-      v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w);
-      break;
-    case EPI_MISH:
-      v.x = mishf_(v.x); v.y = mishf_(v.y); v.z = mishf_(v.z); v.w = mishf_(v.w);
-      break;
-    case EPI_SILU:
-      v.x = siluf_(v.x); v.y = siluf_(v.y); v.z = siluf_(v.z); v.w = siluf_(v.w);
-      break;
-    case EPI_ADDVEC: {
-      const float4 e = *reinterpret_cast<const float4*>(P.evec + (long)g * P.evec_gstride + co);
-      v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
-      break;
-    }
-    case EPI_GATE:
-    case EPI_GEGLU: {
-      if (P.res) {  // pre-activation additive term (DiffNet hoisted conditioner projection)
-        const float4 r = *reinterpret_cast<const float4*>(P.res + g * P.res_gstride + (long)p * P.res_pitch + co);
-        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-      }
-      float2 o;
-      if (P.epi == EPI_GATE) {
-        o.x = sigmoidf_(v.x) * tanhf(v.y);
-        o.y = sigmoidf_(v.z) * tanhf(v.w);
-      } else {
-        o.x = v.x * gelu_erf(v.y);
-        o.y = v.z * gelu_erf(v.w);
-      }
-      *reinterpret_cast<float2*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + (co >> 1)) = o;
-      return;
-    }
-    case EPI_DIFFOUT: {
-      if (co < P.csplit) {
-        float4* o = reinterpret_cast<float4*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + co);
-        float4 x = *o;
-        const float r2 = 0.70710678118654752440f;
-        x.x = (x.x + v.x) * r2; x.y = (x.y + v.y) * r2; x.z = (x.z + v.z) * r2; x.w = (x.w + v.w) * r2;
-        *o = x;
-      } else {
-        float4* o = reinterpret_cast<float4*>(P.out2 + g * P.out2_gstride + (long)p * P.out2_pitch + (co - P.csplit));
-        if (P.accumulate) {
-          float4 s = *o;
-          v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
-        }
-        *o = v;
-      }
-      return;
-    }
-    case EPI_STORE_CF: {
-      float* o = P.out + g * P.out_gstride + (long)co * P.L + p;
-      o[0] = v.x;
-      if (co + 1 < P.Cout) o[(long)P.L] = v.y;
-      if (co + 2 < P.Cout) o[2 * (long)P.L] = v.z;
-      if (co + 3 < P.Cout) o[3 * (long)P.L] = v.w;
-      return;
-    }
-    default: break;
-  }
-  *reinterpret_cast<float4*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + co) = v;
-}
 
 template <int BN>
 __global__ void __launch_bounds__((BN / 8) * 16, (BN == 128 ? 2 : (BN == 64 ? 4 : 6)))
@@ -286,10 +200,7 @@ tapconv_kernel(const __grid_constant__ TapConvParams P) {
 
 
 // Fill geometry-dependent fields (offsets, halo, smem rows) and launch.
-void tapconv_launch(TapConvParams P, cudaStream_t st) {
-  AGPT_CHECK(P.ntaps >= 1 && P.ntaps <= kMaxTaps, "ntaps");
-  AGPT_CHECK(P.cin_pad % TC_KC == 0 && P.cout_pad % 4 == 0, "padding");
-  AGPT_CHECK(P.in_pitch % 1 == 0 && (P.epi == EPI_STORE_CF || P.out_pitch % (P.epi == EPI_GATE || P.epi == EPI_GEGLU ? 2 : 4) == 0), "pitch");
+static void fma_launch(TapConvParams P, cudaStream_t st) {
   int lo = P.tap_off[0], hi = P.tap_off[0];
   for (int t = 1; t < P.ntaps; ++t) { lo = min(lo, P.tap_off[t]); hi = max(hi, P.tap_off[t]); }
   P.lo_al = (lo >= 0) ? (lo / 4) * 4 : -(((-lo) + 3) / 4) * 4;
@@ -312,11 +223,24 @@ void tapconv_launch(TapConvParams P, cudaStream_t st) {
     attr_done = true;
   }
   AGPT_CHECK(smem <= 100 * 1024, "tapconv smem too large (image too wide?)");
+  if (bn == 128) tapconv_kernel<128><<<grid, 256, smem, st>>>(P);
+  else if (bn == 64) tapconv_kernel<64><<<grid, 128, smem, st>>>(P);
+  else tapconv_kernel<32><<<grid, 64, smem, st>>>(P);
+}
+
+// Dispatch: tcgen05 version when the layer has a tensor-core weight image and the operands are
+// 16-byte addressable, else the fp32-FMA version.  Both are sm_100a CUDA; there is no other path.
+void tapconv_launch(TapConvParams P, cudaStream_t st) {
+  AGPT_CHECK(P.ntaps >= 1 && P.ntaps <= kMaxTaps, "ntaps");
+  AGPT_CHECK(P.cin_pad % TC_KC == 0 && P.cout_pad % 4 == 0, "padding");
+  AGPT_CHECK(P.epi == EPI_STORE_CF || P.out_pitch % (P.epi == EPI_GATE || P.epi == EPI_GEGLU ? 2 : 4) == 0, "pitch");
+  const bool tc = tcconv_supported(P);
   ProfRec* rec = nullptr;
   if (g_prof) {
     g_recs.emplace_back();
     rec = &g_recs.back();
-    rec->variant = bn == 128 ? 0 : (bn == 64 ? 1 : 2);
+    const int bn = tc_pick_bn(P.Cout);
+    rec->variant = tc ? 3 : (bn == 128 ? 0 : (bn == 64 ? 1 : 2));
     const double rows = (double)P.G * P.L;
     rec->flops = 2.0 * rows * P.Cin * P.Cout * P.ntaps * (P.flops_scale > 0.f ? P.flops_scale : 1.f);
     const int out_c = (P.epi == EPI_GATE || P.epi == EPI_GEGLU) ? P.Cout / 2 : P.Cout;
@@ -327,13 +251,11 @@ void tapconv_launch(TapConvParams P, cudaStream_t st) {
     AGPT_CUDA(cudaEventCreate(&rec->e1));
     AGPT_CUDA(cudaEventRecord(rec->e0, st));
   }
-  if (bn == 128) tapconv_kernel<128><<<grid, 256, smem, st>>>(P);
-  else if (bn == 64) tapconv_kernel<64><<<grid, 128, smem, st>>>(P);
-  else tapconv_kernel<32><<<grid, 64, smem, st>>>(P);
+  if (tc) tcconv_launch(P, st);
+  else fma_launch(P, st);
   if (rec) AGPT_CUDA(cudaEventRecord(rec->e1, st));
   count_launch(1);
   AGPT_CUDA(cudaGetLastError());
 }
-
 
 }  // namespace agpt

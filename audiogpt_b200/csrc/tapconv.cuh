@@ -54,12 +54,14 @@ struct TapConvParams {
   int epi; const float* res; long res_gstride; int res_pitch; float scale; int accumulate;
   const float* evec; int evec_gstride;
   float* out2; long out2_gstride; int out2_pitch; int csplit;
+  const float* w_tc; int tc_bn, tc_chunks;   // tensor-core weight image (tcconv.cu); tc_bn == 0 => FMA only
   float flops_scale;   // useful fraction of the MACs (zero-padded polyphase taps); 0 => 1
 };
 
 // ---------------------------------------------------------------- host side
 struct PackedConv {
-  DevBuf w, b;
+  DevBuf w, b, w_tc;
+  int tc_bn = 0, tc_chunks = 0;
   int Cin = 0, cin_pad = 0, Cout = 0, cout_pad = 0, ntaps = 0;
   int tap_off_1d[kMaxTaps] = {0};   // for 1-D convs: row offsets; 2-D convs derive offsets from W at launch
   bool is2d = false;
@@ -74,8 +76,14 @@ inline int tc_pick_bn(int cout) {
   return (w128 <= w64) ? 128 : 64;
 }
 
+struct PackedConv;
 // Fill geometry-dependent fields (offsets, halo, smem rows) and launch (tapconv.cu).
 void tapconv_launch(TapConvParams P, cudaStream_t st);
+void tcconv_launch(TapConvParams P, cudaStream_t st);          // tcgen05 version (tcconv.cu)
+bool tcconv_supported(const TapConvParams& P);
+void pack_tc_weights(struct PackedConv& pc, const std::vector<float>& h);
+void tc_set_enabled(int on);
+bool tc_enabled();
 void profile_enable(int on);
 void profile_collect(double* ms, double* flops, double* bytes, long long* launches);
 double fma_peak_tflops();
@@ -99,6 +107,7 @@ inline TapConvParams tapconv_params(const PackedConv& pc, int G, int L, int Wrea
   }
   P.scale = 1.f;
   P.flops_scale = pc.useful;
+  P.w_tc = pc.w_tc.p; P.tc_bn = pc.tc_bn; P.tc_chunks = pc.tc_chunks;
   return P;
 }
 
@@ -114,6 +123,7 @@ inline void pack_conv(PackedConv& pc, const float* w, const float* b, int Cout, 
       for (int k = 0; k < K; ++k)
         h[((size_t)k * pc.cin_pad + ci) * pc.cout_pad + co] = w[((size_t)co * Cin + ci) * K + k] * wscale;
   pc.w.upload(h);
+  pack_tc_weights(pc, h);
   if (!is2d) {
     const int c = (K - 1) / 2;
     for (int k = 0; k < K; ++k) pc.tap_off_1d[k] = k - c;
@@ -164,6 +174,7 @@ inline void pack_convtranspose(PackedConv& pc, const float* w, const float* b, i
     }
   }
   pc.w.upload(h);
+  pack_tc_weights(pc, h);
   pc.useful = (float)(K / (double)u) / (float)pc.ntaps;
   pc.has_bias = b != nullptr;
   std::vector<float> hb(pc.cout_pad, 0.f);

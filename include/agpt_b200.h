@@ -31,11 +31,14 @@ int agpt_version(void);
 long long agpt_launch_count(void);
 void agpt_destroy(agpt_handle h);
 /* Measurement helpers (bench.py): per-launch CUDA-event timing of the tapconv kernel,
- * summed per tile variant v = {0: BN=128, 1: BN=64, 2: BN=32}; and an fp32-FMA
+ * summed per variant v = {0,1,2: fp32-FMA tiles BN=128/64/32; 3: tcgen05 version}; an fp32-FMA
  * saturation probe returning the measured TFLOP/s of the current device.       */
 int agpt_profile_enable(int on);
-int agpt_profile_collect(double ms[3], double flops[3], double bytes[3], long long launches[3]);
+int agpt_profile_collect(double ms[4], double flops[4], double bytes[4], long long launches[4]);
 double agpt_fma_peak_tflops(void);
+/* 1 (default): contractions run on tcgen05 tensor cores with 3xTF32 error compensation;
+ * 0: fp32-FMA kernels only (bit-for-bit the round-1 numerics).                            */
+int agpt_set_tensor_cores(int on);
 
 /* ------------------------------------------------------------------ HiFi-GAN
  * Replaces HifiGanGenerator.__init__/forward/remove_weight_norm
