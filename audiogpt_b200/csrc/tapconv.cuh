@@ -54,7 +54,7 @@ struct TapConvParams {
   int epi; const float* res; long res_gstride; int res_pitch; float scale; int accumulate;
   const float* evec; int evec_gstride;
   float* out2; long out2_gstride; int out2_pitch; int csplit;
-  const float* w_tc; int tc_bn, tc_chunks;   // tensor-core weight image (tcconv.cu); tc_bn == 0 => FMA only
+  const float* w_tc; int tc_bn, tc_chunks, tc_na, tc_nw, tc_flags;   // tensor-core weight image (tcconv.cu); tc_bn == 0 => FMA only
   float flops_scale;   // useful fraction of the MACs (zero-padded polyphase taps); 0 => 1
 };
 
@@ -79,7 +79,8 @@ inline int tc_pick_bn(int cout) {
 struct PackedConv;
 // Fill geometry-dependent fields (offsets, halo, smem rows) and launch (tapconv.cu).
 void tapconv_launch(TapConvParams P, cudaStream_t st);
-void tcconv_launch(TapConvParams P, cudaStream_t st);          // tcgen05 version (tcconv.cu)
+void tcconv_launch(TapConvParams P, cudaStream_t st);          // tcgen05 version (tcconv.cu / tcconv2.cu)
+bool tcconv2_launch(TapConvParams P, cudaStream_t st);
 bool tcconv_supported(const TapConvParams& P);
 void pack_tc_weights(struct PackedConv& pc, const std::vector<float>& h);
 void tc_set_enabled(int on);

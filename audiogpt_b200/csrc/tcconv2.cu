@@ -1,0 +1,286 @@
+// tcconv v2: tcgen05 tapconv with the activation operand staged ONCE per 32-channel chunk.
+//
+// The [128 + halo rows] x [32 ci] activation tile is read from global (coalesced 128-bit loads),
+// passed through the fused prologue, split into TF32 hi/lo parts and written as two K-major
+// SWIZZLE_128B tiles.  A conv tap is then just a different START ROW of the same tile: the UMMA
+// shared-memory descriptor of tap t starts (off_t - off_min) * 128 bytes further (the 128-byte
+// swizzle is a function of the absolute shared-memory address bits, so a row-shifted view of a
+// tile written with the same address-based XOR stays consistent).  Per (chunk, tap) the tensor
+// core runs 4 k-steps x 3 error-compensated products (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo).
+//
+// Warp roles as in tcconv.cu (warps 0-3 transform + epilogue, warp 4 MMA issuer, warp 5 weight
+// producer with cp.async.bulk); NA activation buffers and NW weight stages (chosen on the host
+// from the 227 KB budget) run through full/empty mbarrier rings.
+#include "tapconv.cuh"
+#include "tapconv_epi.cuh"
+#include "tc_common.cuh"
+#include "models.h"
+
+namespace agpt {
+
+namespace {
+
+constexpr int MAX_NA = 4, MAX_NW = 8;
+constexpr int kMaxDyn = 227 * 1024 - 256;   // the kernel also has a small static __shared__ block
+
+struct Tc2Smem {
+  uint32_t a_hi[MAX_NA], a_lo[MAX_NA], w[MAX_NW], rowinfo, bars, tmem_slot, total;
+};
+__host__ __device__ inline void tc2_layout(Tc2Smem& s, int BN, int RRA, int NA, int NW) {
+  uint32_t o = 0;
+  for (int i = 0; i < MAX_NA; ++i) { s.a_hi[i] = o; if (i < NA) o += RRA * 128; }
+  for (int i = 0; i < MAX_NA; ++i) { s.a_lo[i] = o; if (i < NA) o += RRA * 128; }
+  for (int i = 0; i < MAX_NW; ++i) { s.w[i] = o; if (i < NW) o += 2 * BN * 128; }
+  s.rowinfo = o; o += RRA * 4;
+  o = (o + 15) & ~15u;
+  s.bars = o; o += 32 * 8;
+  s.tmem_slot = o; o += 16;
+  s.total = o;
+}
+
+__device__ __forceinline__ float4 pro_apply(const TapConvParams& P, float4 v, bool ok, const float* pv) {
+  if (P.pro == PRO_LRELU) {
+    v.x = lrelu(v.x, P.slope); v.y = lrelu(v.y, P.slope); v.z = lrelu(v.z, P.slope); v.w = lrelu(v.w, P.slope);
+  } else if (P.pro == PRO_ADDVEC) {
+    if (ok) {
+      const float4 a = *reinterpret_cast<const float4*>(pv);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+  } else if (P.pro == PRO_SILU) {
+    v.x = siluf_(v.x); v.y = siluf_(v.y); v.z = siluf_(v.z); v.w = siluf_(v.w);
+  }
+  return v;
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_constant__ TapConvParams P) {
+  extern __shared__ uint8_t smem_raw_[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
+  const int RRA = P.R, NA = P.tc_na, NW = P.tc_nw;
+  __shared__ Tc2Smem S;
+  if (threadIdx.x == 0) tc2_layout(S, BN, RRA, NA, NW);
+  __syncthreads();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S.bars);
+  uint64_t* a_full = bars + 0;            // [MAX_NA]
+  uint64_t* a_empty = bars + MAX_NA;      // [MAX_NA]
+  uint64_t* w_full = bars + 2 * MAX_NA;   // [MAX_NW]
+  uint64_t* w_empty = w_full + MAX_NW;    // [MAX_NW]
+  uint64_t* acc_full = w_empty + MAX_NW;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S.tmem_slot);
+  int* rowinfo = reinterpret_cast<int*>(smem + S.rowinfo);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = blockIdx.z, co0 = blockIdx.y * BN, q0 = blockIdx.x * TC_ROWS;
+  const int Wv = P.Wreal > 0 ? P.Wreal + 1 : 0;
+  const int Lv = Wv ? (P.L / P.Wreal) * Wv : P.L;
+  const int nchunks = P.tc_chunks, ntaps = P.ntaps, total = nchunks * ntaps;
+  const int lo = P.lo_al;
+
+  if (tid == 0) {
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)(BN < 32 ? 32 : BN)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp < 4) {
+    for (int i = tid; i < RRA; i += 128) {
+      const int q = q0 + lo + i;
+      int a = -1;
+      if (q >= 0 && q < Lv) {
+        if (Wv) {
+          const int h = q / Wv, w = q - h * Wv;
+          if (w < P.Wreal) a = (h * P.Wreal + w) * P.in_pitch;
+        } else {
+          a = q * P.in_pitch;
+        }
+      }
+      rowinfo[i] = a;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // =========================== transform warps ===========================
+    const float* __restrict__ ing = P.in + g * P.in_gstride;
+    const float* pvg = (P.pro == PRO_ADDVEC) ? (P.pvec + (long)g * P.pvec_gstride) : nullptr;
+    const int items = RRA * 8;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c % NA, n = c / NA;
+      if (n >= 1) mbar_wait(&a_empty[buf], (uint32_t)((n - 1) & 1));
+      uint8_t* ahi = smem + S.a_hi[buf];
+      uint8_t* alo = smem + S.a_lo[buf];
+      for (int base = tid; base < items; base += 4 * 128) {
+        float4 v[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * 128;
+          ok[u] = false;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (idx < items) {
+            const int row = idx >> 3, ch = c * TC_KCH + 4 * (idx & 7);
+            const int a = rowinfo[row];
+            ok[u] = (a >= 0) && (ch < P.Cin);
+            if (ok[u]) v[u] = __ldg(reinterpret_cast<const float4*>(ing + a + ch));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * 128;
+          if (idx < items) {
+            const int row = idx >> 3, j = idx & 7;
+            const float4 x = pro_apply(P, v[u], ok[u], pvg ? (pvg + c * TC_KCH + 4 * j) : nullptr);
+            const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+            const float4 l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+            const uint32_t o = sw128(row, j);
+            *reinterpret_cast<float4*>(ahi + o) = h;
+            *reinterpret_cast<float4*>(alo + o) = l;
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&a_full[buf]);
+    }
+    // =========================== epilogue ===========================
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int q = q0 + tid;
+    bool valid = q < Lv;
+    int p = q;
+    if (valid && Wv) {
+      const int h = q / Wv, w = q - h * Wv;
+      valid = w < P.Wreal;
+      p = h * P.Wreal + w;
+    }
+#pragma unroll 1
+    for (int cb = 0; cb < BN; cb += 32) {
+      uint32_t rg[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(rg[0]), "=r"(rg[1]), "=r"(rg[2]), "=r"(rg[3]), "=r"(rg[4]), "=r"(rg[5]), "=r"(rg[6]), "=r"(rg[7]),
+            "=r"(rg[8]), "=r"(rg[9]), "=r"(rg[10]), "=r"(rg[11]), "=r"(rg[12]), "=r"(rg[13]), "=r"(rg[14]), "=r"(rg[15]),
+            "=r"(rg[16]), "=r"(rg[17]), "=r"(rg[18]), "=r"(rg[19]), "=r"(rg[20]), "=r"(rg[21]), "=r"(rg[22]), "=r"(rg[23]),
+            "=r"(rg[24]), "=r"(rg[25]), "=r"(rg[26]), "=r"(rg[27]), "=r"(rg[28]), "=r"(rg[29]), "=r"(rg[30]), "=r"(rg[31])
+          : "r"(taddr) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (valid) {
+#pragma unroll
+        for (int qd = 0; qd < 8; ++qd) {
+          tc_epilogue(P, g, p, co0 + cb + 4 * qd,
+                      make_float4(__uint_as_float(rg[4 * qd]), __uint_as_float(rg[4 * qd + 1]),
+                                  __uint_as_float(rg[4 * qd + 2]), __uint_as_float(rg[4 * qd + 3])));
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+      const bool use_base_off = (P.tc_flags & 1) != 0;
+      int it = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        const int buf = c % NA;
+        mbar_wait(&a_full[buf], (uint32_t)((c / NA) & 1));
+        tc_fence_after();
+        const uint32_t ahi0 = smem_u32(smem + S.a_hi[buf]), alo0 = smem_u32(smem + S.a_lo[buf]);
+        for (int t = 0; t < ntaps; ++t, ++it) {
+          const int s = it % NW;
+          mbar_wait(&w_full[s], (uint32_t)((it / NW) & 1));
+          tc_fence_after();
+          const uint32_t shift = (uint32_t)(P.tap_off[t] - lo) * 128u;
+          uint64_t dah = make_desc(ahi0 + shift), dal = make_desc(alo0 + shift);
+          if (use_base_off) {
+            const uint64_t bo = (uint64_t)(((ahi0 + shift) >> 7) & 7) << 49;   // matrix base offset field
+            dah |= bo;
+            dal |= (uint64_t)(((alo0 + shift) >> 7) & 7) << 49;
+          }
+          const uint64_t dwh = make_desc(smem_u32(smem + S.w[s]));
+          const uint64_t dwl = make_desc(smem_u32(smem + S.w[s] + BN * 128));
+#pragma unroll
+          for (int k = 0; k < TC_KCH / 8; ++k) {
+            const uint64_t ko = (uint64_t)((k * 32) >> 4);
+            umma_tf32(tmem_base, dah + ko, dwh + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_tf32(tmem_base, dal + ko, dwh + ko, idesc, 1u);
+            umma_tf32(tmem_base, dah + ko, dwl + ko, idesc, 1u);
+          }
+          umma_commit(&w_empty[s]);
+        }
+        umma_commit(&a_empty[buf]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // =========================== weight producer ===========================
+    if (lane == 0) {
+      const uint32_t bytes = 2u * BN * 128u;
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(P.w_tc) + (size_t)blockIdx.y * (size_t)total * bytes;
+      for (int it = 0; it < total; ++it) {
+        const int s = it % NW, n = it / NW;
+        if (n >= 1) mbar_wait(&w_empty[s], (uint32_t)((n - 1) & 1));
+        mbar_arrive_expect_tx(&w_full[s], bytes);
+        bulk_g2s(smem + S.w[s], wsrc + (size_t)it * bytes, bytes, &w_full[s]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(BN < 32 ? 32 : BN)) : "memory");
+  }
+}
+
+}  // namespace
+
+// returns false when the shape does not fit the shared-memory budget (caller falls back to v1)
+bool tcconv2_launch(TapConvParams P, cudaStream_t st) {
+  int lo = P.tap_off[0], hi = P.tap_off[0];
+  for (int t = 1; t < P.ntaps; ++t) { lo = std::min(lo, P.tap_off[t]); hi = std::max(hi, P.tap_off[t]); }
+  P.lo_al = lo;
+  const int RRA = round_up(TC_ROWS + (hi - lo), 8);
+  P.R = RRA;
+  const int BN = P.tc_bn;
+  const long avail = (long)kMaxDyn - 1024 /*align*/ - (RRA * 4 + 512) /*rowinfo+barriers*/;
+  const long abytes = 2L * RRA * 128, wbytes = 2L * BN * 128;
+  int NA = (P.ntaps == 1) ? 3 : 2;
+  NA = std::min(NA, P.tc_chunks);
+  while (NA > 1 && NA * abytes + 2 * wbytes > avail) --NA;
+  if (NA * abytes + 2 * wbytes > avail) return false;
+  int NW = (int)std::min<long>(MAX_NW, (avail - NA * abytes) / wbytes);
+  NW = std::min(NW, std::max(2, P.tc_chunks * P.ntaps));
+  P.tc_na = NA; P.tc_nw = NW;
+  Tc2Smem S;
+  tc2_layout(S, BN, RRA, NA, NW);
+  const size_t smem = (size_t)S.total + 1024;
+  if (smem > (size_t)kMaxDyn) return false;
+  const int Wv = P.Wreal > 0 ? P.Wreal + 1 : 0;
+  const int Lv = Wv ? (P.L / P.Wreal) * Wv : P.L;
+  dim3 grid(cdiv(Lv, TC_ROWS), cdiv(P.Cout, BN), P.G);
+  int dev = 0;
+  AGPT_CUDA(cudaGetDevice(&dev));
+  static bool attr_done_dev[64] = {false};
+  if (!attr_done_dev[dev & 63]) {
+    AGPT_CUDA(cudaFuncSetAttribute(tcconv2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
+    AGPT_CUDA(cudaFuncSetAttribute(tcconv2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
+    AGPT_CUDA(cudaFuncSetAttribute(tcconv2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
+    attr_done_dev[dev & 63] = true;
+  }
+  if (BN == 128) tcconv2_kernel<128><<<grid, TC_THREADS, smem, st>>>(P);
+  else if (BN == 64) tcconv2_kernel<64><<<grid, TC_THREADS, smem, st>>>(P);
+  else tcconv2_kernel<32><<<grid, TC_THREADS, smem, st>>>(P);
+  return true;
+}
+
+}  // namespace agpt
