@@ -1,30 +1,53 @@
-// Shared fused epilogue of the tapconv kernels (fp32 FMA version and tcgen05 version):
-// one call handles 4 consecutive output channels of one output row.
+// Shared fused epilogue of the tapconv kernels (fp32 FMA version and tcgen05 versions):
+// one call handles 4 consecutive output channels of one output row.  Split in two phases so
+// that a kernel can issue the global READS of several items (residual, old accumulator) before
+// consuming any of them (memory-level parallelism in the tcgen05 epilogue).
 #pragma once
 #include "tapconv.cuh"
 
 namespace agpt {
 
-__device__ __forceinline__ void tc_epilogue(const TapConvParams& P, int g, int p, int co, float4 v) {
+struct EpiPre {
+  float4 a;   // residual / pre-activation additive term / old x (DIFFOUT, co < csplit) / old skip (co >= csplit)
+  float4 b;   // old accumulator (EPI_ACC with accumulate)
+};
+
+__device__ __forceinline__ void epi_load(const TapConvParams& P, int g, int p, int co, EpiPre& pre) {
+  pre.a = make_float4(0.f, 0.f, 0.f, 0.f);
+  pre.b = pre.a;
+  if (co >= P.Cout) return;
+  switch (P.epi) {
+    case EPI_RES:
+    case EPI_ACC:
+    case EPI_GATE:
+    case EPI_GEGLU:
+      if (P.res) pre.a = __ldg(reinterpret_cast<const float4*>(P.res + g * P.res_gstride + (long)p * P.res_pitch + co));
+      if (P.epi == EPI_ACC && P.accumulate)
+        pre.b = *reinterpret_cast<const float4*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + co);
+      break;
+    case EPI_DIFFOUT:
+      if (co < P.csplit) pre.a = *reinterpret_cast<const float4*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + co);
+      else if (P.accumulate)
+        pre.a = *reinterpret_cast<const float4*>(P.out2 + g * P.out2_gstride + (long)p * P.out2_pitch + (co - P.csplit));
+      break;
+    default: break;
+  }
+}
+
+__device__ __forceinline__ void epi_store(const TapConvParams& P, int g, int p, int co, float4 v, const EpiPre& pre) {
   if (co >= P.Cout) return;
   if (P.bias) {
-    const float4 b = *reinterpret_cast<const float4*>(P.bias + co);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + co));
     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
   }
   switch (P.epi) {
     case EPI_BIAS: break;
     case EPI_RES:
     case EPI_ACC: {
-      if (P.res) {
-        const float4 r = *reinterpret_cast<const float4*>(P.res + g * P.res_gstride + (long)p * P.res_pitch + co);
-        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-      }
+      v.x += pre.a.x; v.y += pre.a.y; v.z += pre.a.z; v.w += pre.a.w;
       if (P.epi == EPI_ACC) {
         v.x *= P.scale; v.y *= P.scale; v.z *= P.scale; v.w *= P.scale;
-        if (P.accumulate) {
-          const float4 o = *reinterpret_cast<const float4*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + co);
-          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-        }
+        v.x += pre.b.x; v.y += pre.b.y; v.z += pre.b.z; v.w += pre.b.w;
       }
       break;
     }
@@ -41,16 +64,13 @@ __device__ __forceinline__ void tc_epilogue(const TapConvParams& P, int g, int p
       v.x = siluf_(v.x); v.y = siluf_(v.y); v.z = siluf_(v.z); v.w = siluf_(v.w);
       break;
     case EPI_ADDVEC: {
-      const float4 e = *reinterpret_cast<const float4*>(P.evec + (long)g * P.evec_gstride + co);
+      const float4 e = __ldg(reinterpret_cast<const float4*>(P.evec + (long)g * P.evec_gstride + co));
       v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
       break;
     }
     case EPI_GATE:
     case EPI_GEGLU: {
-      if (P.res) {  // pre-activation additive term (DiffNet hoisted conditioner projection)
-        const float4 r = *reinterpret_cast<const float4*>(P.res + g * P.res_gstride + (long)p * P.res_pitch + co);
-        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-      }
+      v.x += pre.a.x; v.y += pre.a.y; v.z += pre.a.z; v.w += pre.a.w;   // pre-activation term (DiffNet conditioner)
       float2 o;
       if (P.epi == EPI_GATE) {
         o.x = sigmoidf_(v.x) * tanhf(v.y);
@@ -64,18 +84,12 @@ __device__ __forceinline__ void tc_epilogue(const TapConvParams& P, int g, int p
     }
     case EPI_DIFFOUT: {
       if (co < P.csplit) {
-        float4* o = reinterpret_cast<float4*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + co);
-        float4 x = *o;
         const float r2 = 0.70710678118654752440f;
-        x.x = (x.x + v.x) * r2; x.y = (x.y + v.y) * r2; x.z = (x.z + v.z) * r2; x.w = (x.w + v.w) * r2;
-        *o = x;
+        const float4 x = make_float4((pre.a.x + v.x) * r2, (pre.a.y + v.y) * r2, (pre.a.z + v.z) * r2, (pre.a.w + v.w) * r2);
+        *reinterpret_cast<float4*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + co) = x;
       } else {
-        float4* o = reinterpret_cast<float4*>(P.out2 + g * P.out2_gstride + (long)p * P.out2_pitch + (co - P.csplit));
-        if (P.accumulate) {
-          float4 s = *o;
-          v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
-        }
-        *o = v;
+        v.x += pre.a.x; v.y += pre.a.y; v.z += pre.a.z; v.w += pre.a.w;   // zeros unless accumulate
+        *reinterpret_cast<float4*>(P.out2 + g * P.out2_gstride + (long)p * P.out2_pitch + (co - P.csplit)) = v;
       }
       return;
     }
@@ -90,6 +104,12 @@ __device__ __forceinline__ void tc_epilogue(const TapConvParams& P, int g, int p
     default: break;
   }
   *reinterpret_cast<float4*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + co) = v;
+}
+
+__device__ __forceinline__ void tc_epilogue(const TapConvParams& P, int g, int p, int co, float4 v) {
+  EpiPre pre;
+  epi_load(P, g, p, co, pre);
+  epi_store(P, g, p, co, v, pre);
 }
 
 }  // namespace agpt

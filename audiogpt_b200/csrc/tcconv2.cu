@@ -24,14 +24,16 @@ constexpr int MAX_NA = 4, MAX_NW = 8;
 constexpr int kMaxDyn = 227 * 1024 - 256;   // the kernel also has a small static __shared__ block
 
 struct Tc2Smem {
-  uint32_t a_hi[MAX_NA], a_lo[MAX_NA], w[MAX_NW], rowinfo, bars, tmem_slot, total;
+  uint32_t a_hi[MAX_NA], a_lo[MAX_NA], w[MAX_NW], raw[2], rowinfo, rowp, bars, tmem_slot, total;
 };
-__host__ __device__ inline void tc2_layout(Tc2Smem& s, int BN, int RRA, int NA, int NW) {
+__host__ __device__ inline void tc2_layout(Tc2Smem& s, int BN, int RRA, int NA, int NW, int NR) {
   uint32_t o = 0;
   for (int i = 0; i < MAX_NA; ++i) { s.a_hi[i] = o; if (i < NA) o += RRA * 128; }
   for (int i = 0; i < MAX_NA; ++i) { s.a_lo[i] = o; if (i < NA) o += RRA * 128; }
   for (int i = 0; i < MAX_NW; ++i) { s.w[i] = o; if (i < NW) o += 2 * BN * 128; }
+  for (int i = 0; i < 2; ++i) { s.raw[i] = o; if (i < NR) o += RRA * 128; }
   s.rowinfo = o; o += RRA * 4;
+  s.rowp = o; o += TC_ROWS * 4;
   o = (o + 15) & ~15u;
   s.bars = o; o += 32 * 8;
   s.tmem_slot = o; o += 16;
@@ -57,9 +59,9 @@ template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_constant__ TapConvParams P) {
   extern __shared__ uint8_t smem_raw_[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
-  const int RRA = P.R, NA = P.tc_na, NW = P.tc_nw;
+  const int RRA = P.R, NA = P.tc_na, NW = P.tc_nw, NR = P.tc_nr;
   __shared__ Tc2Smem S;
-  if (threadIdx.x == 0) tc2_layout(S, BN, RRA, NA, NW);
+  if (threadIdx.x == 0) tc2_layout(S, BN, RRA, NA, NW, NR);
   __syncthreads();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S.bars);
   uint64_t* a_full = bars + 0;            // [MAX_NA]
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
   uint64_t* acc_full = w_empty + MAX_NW;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S.tmem_slot);
   int* rowinfo = reinterpret_cast<int*>(smem + S.rowinfo);
+  int* rowp = reinterpret_cast<int*>(smem + S.rowp);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = blockIdx.z, co0 = blockIdx.y * BN, q0 = blockIdx.x * TC_ROWS;
@@ -102,6 +105,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
       }
       rowinfo[i] = a;
     }
+    {  // output row -> real position (or -1)
+      const int q = q0 + tid;
+      int p = -1;
+      if (q < Lv) {
+        if (Wv) {
+          const int h = q / Wv, w = q - h * Wv;
+          if (w < P.Wreal) p = h * P.Wreal + w;
+        } else {
+          p = q;
+        }
+      }
+      rowp[tid] = p;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -113,56 +129,73 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
     const float* __restrict__ ing = P.in + g * P.in_gstride;
     const float* pvg = (P.pro == PRO_ADDVEC) ? (P.pvec + (long)g * P.pvec_gstride) : nullptr;
     const int items = RRA * 8;
+    auto issue_raw = [&](int c, int rb) {
+      uint8_t* dst = smem + S.raw[rb];
+      for (int idx = tid; idx < items; idx += 128) {
+        const int row = idx >> 3, j = idx & 7;
+        const int ch = c * TC_KCH + 4 * j;
+        const int a = rowinfo[row];
+        const bool ok = (a >= 0) && (ch < P.Cin);
+        cp_async16_zfill(dst + sw128(row, j), ok ? (ing + a + ch) : P.in, ok ? 16u : 0u);
+      }
+      cp_async_commit_();
+    };
+    issue_raw(0, 0);
+    if (NR == 2 && nchunks > 1) issue_raw(1, 1);
     for (int c = 0; c < nchunks; ++c) {
       const int buf = c % NA, n = c / NA;
+      const int rb = (NR == 2) ? (c & 1) : 0;
+      // raw(c) landed?  (with NR == 2 one younger group -- raw(c+1) -- may still be in flight)
+      if (NR == 2 && c + 1 < nchunks) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else cp_async_wait_all_();
+      named_bar_sync(1, 128);
       if (n >= 1) mbar_wait(&a_empty[buf], (uint32_t)((n - 1) & 1));
       uint8_t* ahi = smem + S.a_hi[buf];
       uint8_t* alo = smem + S.a_lo[buf];
-      for (int base = tid; base < items; base += 4 * 128) {
-        float4 v[4];
-        bool ok[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int idx = base + u * 128;
-          ok[u] = false;
-          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (idx < items) {
-            const int row = idx >> 3, ch = c * TC_KCH + 4 * (idx & 7);
-            const int a = rowinfo[row];
-            ok[u] = (a >= 0) && (ch < P.Cin);
-            if (ok[u]) v[u] = __ldg(reinterpret_cast<const float4*>(ing + a + ch));
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int idx = base + u * 128;
-          if (idx < items) {
-            const int row = idx >> 3, j = idx & 7;
-            const float4 x = pro_apply(P, v[u], ok[u], pvg ? (pvg + c * TC_KCH + 4 * j) : nullptr);
-            const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
-            const float4 l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-            const uint32_t o = sw128(row, j);
-            *reinterpret_cast<float4*>(ahi + o) = h;
-            *reinterpret_cast<float4*>(alo + o) = l;
-          }
-        }
+      const uint8_t* rawb = smem + S.raw[rb];
+#pragma unroll 2
+      for (int idx = tid; idx < items; idx += 128) {
+        const int row = idx >> 3, j = idx & 7;
+        const uint32_t o = sw128(row, j);
+        const float4 v = *reinterpret_cast<const float4*>(rawb + o);
+        const bool ok = (P.pro == PRO_ADDVEC) ? (rowinfo[row] >= 0 && (c * TC_KCH + 4 * j) < P.Cin) : true;
+        const float4 x = pro_apply(P, v, ok, pvg ? (pvg + c * TC_KCH + 4 * j) : nullptr);
+        const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+        const float4 l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        *reinterpret_cast<float4*>(ahi + o) = h;
+        *reinterpret_cast<float4*>(alo + o) = l;
       }
       fence_proxy_async();
       mbar_arrive(&a_full[buf]);
+      // refill the raw buffer just consumed
+      const int cn = c + NR;
+      if (cn < nchunks) {
+        named_bar_sync(1, 128);          // everyone finished reading raw[rb]
+        issue_raw(cn, rb);
+      }
     }
     // =========================== epilogue ===========================
+    // TMEM -> registers -> swizzled staging block [128 rows][32 cols] in shared memory (the operand
+    // buffers are free now) -> coalesced (row, 16-byte chunk) items through the fused epilogue.
+    // 8 (row, 16-byte chunk) items per thread and 32-column block.  The global READS of a block
+    // (residual / old accumulator) are issued one block ahead -- for block 0 even before the
+    // accumulator is complete -- so their latency overlaps the tail of the main loop.
+    EpiPre pre[8];
+    int pp[8];
+    auto load_block = [&](int cb) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = tid + i * 128;
+        pp[i] = rowp[idx >> 3];
+        if (pp[i] >= 0) epi_load(P, g, pp[i], co0 + cb + 4 * (idx & 7), pre[i]);
+      }
+    };
+    load_block(0);
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const int q = q0 + tid;
-    bool valid = q < Lv;
-    int p = q;
-    if (valid && Wv) {
-      const int h = q / Wv, w = q - h * Wv;
-      valid = w < P.Wreal;
-      p = h * P.Wreal + w;
-    }
+    uint8_t* stg0 = smem + S.a_hi[0];            // 2 x 16 KB inside the first operand buffers (>= 32 KB)
 #pragma unroll 1
-    for (int cb = 0; cb < BN; cb += 32) {
+    for (int cb = 0, blk = 0; cb < BN; cb += 32, ++blk) {
       uint32_t rg[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb;
       asm volatile(
@@ -175,14 +208,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
             "=r"(rg[24]), "=r"(rg[25]), "=r"(rg[26]), "=r"(rg[27]), "=r"(rg[28]), "=r"(rg[29]), "=r"(rg[30]), "=r"(rg[31])
           : "r"(taddr) : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (valid) {
+      uint8_t* stg = stg0 + (blk & 1) * (TC_ROWS * 128);
 #pragma unroll
-        for (int qd = 0; qd < 8; ++qd) {
-          tc_epilogue(P, g, p, co0 + cb + 4 * qd,
-                      make_float4(__uint_as_float(rg[4 * qd]), __uint_as_float(rg[4 * qd + 1]),
-                                  __uint_as_float(rg[4 * qd + 2]), __uint_as_float(rg[4 * qd + 3])));
-        }
+      for (int qd = 0; qd < 8; ++qd)
+        *reinterpret_cast<float4*>(stg + sw128(tid, qd)) =
+            make_float4(__uint_as_float(rg[4 * qd]), __uint_as_float(rg[4 * qd + 1]),
+                        __uint_as_float(rg[4 * qd + 2]), __uint_as_float(rg[4 * qd + 3]));
+      named_bar_sync(1, 128);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = tid + i * 128;
+        const int row = idx >> 3, j = idx & 7;
+        if (pp[i] >= 0)
+          epi_store(P, g, pp[i], co0 + cb + 4 * j, *reinterpret_cast<const float4*>(stg + sw128(row, j)), pre[i]);
       }
+      if (cb + 32 < BN) load_block(cb + 32);
+      // staging halves alternate; a half is rewritten two blocks later, after the next named
+      // barrier, so no extra barrier is needed here
     }
   } else if (warp == 4) {
     // =========================== MMA issuer ===========================
@@ -252,17 +294,24 @@ bool tcconv2_launch(TapConvParams P, cudaStream_t st) {
   const int RRA = round_up(TC_ROWS + (hi - lo), 8);
   P.R = RRA;
   const int BN = P.tc_bn;
-  const long avail = (long)kMaxDyn - 1024 /*align*/ - (RRA * 4 + 512) /*rowinfo+barriers*/;
+  const long avail = (long)kMaxDyn - 1024 /*align*/ - (RRA * 4 + TC_ROWS * 4 + 512) /*row tables + barriers*/;
   const long abytes = 2L * RRA * 128, wbytes = 2L * BN * 128;
+  const long rbytes = (long)RRA * 128;
+  const int iters = P.tc_chunks * P.ntaps;
   int NA = (P.ntaps == 1) ? 3 : 2;
-  NA = std::min(NA, P.tc_chunks);
-  while (NA > 1 && NA * abytes + 2 * wbytes > avail) --NA;
-  if (NA * abytes + 2 * wbytes > avail) return false;
-  int NW = (int)std::min<long>(MAX_NW, (avail - NA * abytes) / wbytes);
-  NW = std::min(NW, std::max(2, P.tc_chunks * P.ntaps));
-  P.tc_na = NA; P.tc_nw = NW;
+  NA = std::max(2, std::min(NA, std::max(2, P.tc_chunks)));   // >= 2: the epilogue stages through 32 KB of it
+  int NR = 1;
+  if (NA * abytes + rbytes + 2 * wbytes > avail) return false;
+  int NW = (int)std::min<long>(MAX_NW, (avail - NA * abytes - rbytes) / wbytes);
+  // a second raw buffer only if it does not cost weight stages we need
+  if (P.tc_chunks > 1) {
+    const int nw2 = (int)std::min<long>(MAX_NW, (avail - NA * abytes - 2 * rbytes) / wbytes);
+    if (nw2 >= std::min(4, iters)) { NR = 2; NW = nw2; }
+  }
+  NW = std::max(2, std::min(NW, std::max(2, iters)));
+  P.tc_na = NA; P.tc_nw = NW; P.tc_nr = NR;
   Tc2Smem S;
-  tc2_layout(S, BN, RRA, NA, NW);
+  tc2_layout(S, BN, RRA, NA, NW, NR);
   const size_t smem = (size_t)S.total + 1024;
   if (smem > (size_t)kMaxDyn) return false;
   const int Wv = P.Wreal > 0 ? P.Wreal + 1 : 0;
