@@ -164,4 +164,9 @@ int agpt_unet_ddim_sample(agpt_handle h, const float* x_T, int B, int H, int W, 
   });
 }
 
+int agpt_bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, int epi_res, int use_tc, int reps,
+                       int check, double* out3, double* dbg8_or_null) {
+  return guarded([&] { bench_tapconv(G, L, Cin, Cout, K, dil, Wreal, epi_res, use_tc, reps, check, out3, dbg8_or_null); });
+}
+
 }  // extern "C"

@@ -28,4 +28,7 @@ void unet_ddim_sample(Handle* h, const float* x_T, int B, int H, int W, int S, c
                       const float* a_t, const float* a_prev, const float* sigma, const float* sqrt_om,
                       float cfg_scale, float* x_out, cudaStream_t st);
 
+void bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, int epi_res, int use_tc, int reps,
+                   int check, double* out, double* dbg_avg);
+
 }  // namespace agpt

@@ -308,9 +308,11 @@ void tcconv_launch(TapConvParams P, cudaStream_t st) {
     ver = (e && e[0] == '1') ? 1 : 2;
     const char* b = getenv("AGPT_TC_BO");
     bo = (b && b[0] == '1') ? 1 : 0;
+    const char* d = getenv("AGPT_TC_DBGFLAGS");     // experiment switches (bits 2..): see tcconv2.cu
+    if (d) bo |= atoi(d) & ~3;
   }
   if (ver == 2) {
-    P.tc_flags = bo;
+    P.tc_flags = bo | P.tc_flags_user;
     if (tcconv2_launch(P, st)) return;
   }
   int lo = P.tap_off[0], hi = P.tap_off[0];

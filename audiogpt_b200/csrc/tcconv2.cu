@@ -79,6 +79,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
   const int Lv = Wv ? (P.L / P.Wreal) * Wv : P.L;
   const int nchunks = P.tc_chunks, ntaps = P.ntaps, total = nchunks * ntaps;
   const int lo = P.lo_al;
+  const bool dbg_on = (P.tc_flags & 2) && P.dbg;
+  long long* dbg = dbg_on ? P.dbg + 8 * ((long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+  if (dbg_on && tid == 0) dbg[0] = clock64();
 
   if (tid == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
@@ -123,6 +126,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg_on && tid == 0) dbg[1] = clock64();
 
   if (warp < 4) {
     // =========================== transform warps ===========================
@@ -142,6 +146,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
     };
     issue_raw(0, 0);
     if (NR == 2 && nchunks > 1) issue_raw(1, 1);
+    {  // pull the epilogue's global operands (residual / old accumulator) into L2 while the main loop runs
+      const float* pf0 = nullptr; long gs0 = 0; int pitch0 = 0;
+      const float* pf1 = nullptr; long gs1 = 0; int pitch1 = 0;
+      if ((P.epi == EPI_RES || P.epi == EPI_ACC || P.epi == EPI_GATE || P.epi == EPI_GEGLU) && P.res) {
+        pf0 = P.res; gs0 = P.res_gstride; pitch0 = P.res_pitch;
+      }
+      if (P.epi == EPI_ACC && P.accumulate) { pf1 = P.out; gs1 = P.out_gstride; pitch1 = P.out_pitch; }
+      if (P.epi == EPI_DIFFOUT) { pf0 = P.out; gs0 = P.out_gstride; pitch0 = P.out_pitch; }
+      const int lines = (BN * 4) / 128 > 0 ? (BN * 4) / 128 : 1;     // 128-byte lines per output row
+      for (int idx = tid; idx < TC_ROWS * lines; idx += 128) {
+        const int p = rowp[idx / lines];
+        const int co = co0 + (idx % lines) * 32;
+        if (p >= 0 && co < P.Cout) {
+          if (pf0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf0 + g * gs0 + (long)p * pitch0 + co));
+          if (pf1) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf1 + g * gs1 + (long)p * pitch1 + co));
+        }
+      }
+    }
     for (int c = 0; c < nchunks; ++c) {
       const int buf = c % NA, n = c / NA;
       const int rb = (NR == 2) ? (c & 1) : 0;
@@ -187,12 +209,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
       for (int i = 0; i < 8; ++i) {
         const int idx = tid + i * 128;
         pp[i] = rowp[idx >> 3];
+        if (P.tc_flags & 4) { pre[i].a = make_float4(0.f, 0.f, 0.f, 0.f); pre[i].b = pre[i].a; continue; }   // experiment: no global reads
         if (pp[i] >= 0) epi_load(P, g, pp[i], co0 + cb + 4 * (idx & 7), pre[i]);
       }
     };
     load_block(0);
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    if (dbg_on && tid == 0) dbg[4] = clock64();
     uint8_t* stg0 = smem + S.a_hi[0];            // 2 x 16 KB inside the first operand buffers (>= 32 KB)
 #pragma unroll 1
     for (int cb = 0, blk = 0; cb < BN; cb += 32, ++blk) {
@@ -219,28 +243,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
       for (int i = 0; i < 8; ++i) {
         const int idx = tid + i * 128;
         const int row = idx >> 3, j = idx & 7;
-        if (pp[i] >= 0)
+        if (pp[i] >= 0 && !((P.tc_flags & 8) && (row & 63) != 0))   // experiment bit 8: store 2 rows only
           epi_store(P, g, pp[i], co0 + cb + 4 * j, *reinterpret_cast<const float4*>(stg + sw128(row, j)), pre[i]);
       }
       if (cb + 32 < BN) load_block(cb + 32);
       // staging halves alternate; a half is rewritten two blocks later, after the next named
       // barrier, so no extra barrier is needed here
     }
+    if (dbg_on && tid == 0) dbg[5] = clock64();
   } else if (warp == 4) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
       const bool use_base_off = (P.tc_flags & 1) != 0;
+      long long dbg_wa = 0, dbg_ww = 0;
       int it = 0;
       for (int c = 0; c < nchunks; ++c) {
         const int buf = c % NA;
+        long long tw0 = dbg_on ? clock64() : 0;
         mbar_wait(&a_full[buf], (uint32_t)((c / NA) & 1));
         tc_fence_after();
+        if (dbg_on) { const long long t1 = clock64(); if (c == 0) dbg[2] = t1; dbg_wa += t1 - tw0; }
         const uint32_t ahi0 = smem_u32(smem + S.a_hi[buf]), alo0 = smem_u32(smem + S.a_lo[buf]);
         for (int t = 0; t < ntaps; ++t, ++it) {
           const int s = it % NW;
+          tw0 = dbg_on ? clock64() : 0;
           mbar_wait(&w_full[s], (uint32_t)((it / NW) & 1));
           tc_fence_after();
+          if (dbg_on) dbg_ww += clock64() - tw0;
           const uint32_t shift = (uint32_t)(P.tap_off[t] - lo) * 128u;
           uint64_t dah = make_desc(ahi0 + shift), dal = make_desc(alo0 + shift);
           if (use_base_off) {
@@ -262,6 +292,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
         umma_commit(&a_empty[buf]);
       }
       umma_commit(acc_full);
+      if (dbg_on) { dbg[3] = clock64(); dbg[6] = dbg_wa; dbg[7] = dbg_ww; }
     }
   } else {
     // =========================== weight producer ===========================
@@ -299,12 +330,16 @@ bool tcconv2_launch(TapConvParams P, cudaStream_t st) {
   const long rbytes = (long)RRA * 128;
   const int iters = P.tc_chunks * P.ntaps;
   int NA = (P.ntaps == 1) ? 3 : 2;
-  NA = std::max(2, std::min(NA, std::max(2, P.tc_chunks)));   // >= 2: the epilogue stages through 32 KB of it
-  int NR = 1;
-  if (NA * abytes + rbytes + 2 * wbytes > avail) return false;
-  int NW = (int)std::min<long>(MAX_NW, (avail - NA * abytes - rbytes) / wbytes);
-  // a second raw buffer only if it does not cost weight stages we need
-  if (P.tc_chunks > 1) {
+  NA = std::max(2, std::min(NA, std::max(2, P.tc_chunks)));
+  int NR = (P.ntaps == 1 && P.tc_chunks > 1) ? 2 : 1;
+  auto fits = [&](int na, int nr, int nw) { return na * abytes + nr * rbytes + nw * wbytes <= avail; };
+  // the epilogue stages through the first 32 KB of the operand buffers
+  if (!fits(NA, NR, 2) && NR == 2) NR = 1;
+  if (!fits(NA, NR, 2) && NA == 3) NA = 2;
+  if (!fits(NA, NR, 2) && (long)RRA * 128 >= 32768) NA = 1;
+  if (!fits(NA, NR, 2)) return false;
+  int NW = (int)std::min<long>(MAX_NW, (avail - NA * abytes - NR * rbytes) / wbytes);
+  if (NR == 1 && P.tc_chunks > 1) {   // a second raw buffer when it leaves >= 4 weight stages
     const int nw2 = (int)std::min<long>(MAX_NW, (avail - NA * abytes - 2 * rbytes) / wbytes);
     if (nw2 >= std::min(4, iters)) { NR = 2; NW = nw2; }
   }

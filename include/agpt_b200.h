@@ -39,6 +39,12 @@ double agpt_fma_peak_tflops(void);
 /* 1 (default): contractions run on tcgen05 tensor cores with 3xTF32 error compensation;
  * 0: fp32-FMA kernels only (bit-for-bit the round-1 numerics).                            */
 int agpt_set_tensor_cores(int on);
+/* Micro-benchmark of one tapconv layer (random data): out3 = {ms per launch, algorithmic TFLOP/s,
+ * max |tcgen05 - fp32 FMA| when check != 0}; dbg8 (tcgen05 only) = average per-CTA phase cycles
+ * {setup, first activation tile, MMA issue loop, drain, epilogue, total, wait-on-activations,
+ * wait-on-weights}.  Wreal > 0 selects a 3x3 conv on an (L/Wreal) x Wreal image.              */
+int agpt_bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, int epi_res, int use_tc,
+                       int reps, int check, double* out3, double* dbg8_or_null);
 
 /* ------------------------------------------------------------------ HiFi-GAN
  * Replaces HifiGanGenerator.__init__/forward/remove_weight_norm
