@@ -57,6 +57,8 @@ void bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, i
   out[0] = ms / reps;
   out[1] = 2.0 * G * (double)L * Cin * Cout * taps / (out[0] * 1e-3) / 1e12;
   out[2] = -1.0;
+  const char* tcv = getenv("AGPT_TC_V");
+  const bool raw_dbg = !(tcv && atoi(tcv) < 3);
   if (dbg_avg && use_tc) {
     std::vector<long long> h((size_t)nctas * 8);
     AGPT_CUDA(cudaMemcpy(h.data(), dbgbuf.p, h.size() * 8, cudaMemcpyDeviceToHost));
@@ -64,7 +66,13 @@ void bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, i
     long n = 0;
     for (long c = 0; c < nctas; ++c) {
       const long long* d = &h[c * 8];
-      if (d[0] == 0 || d[5] == 0) continue;
+      if (d[0] == 0) continue;
+      if (raw_dbg) {                      // v3: the kernel already stores durations
+        for (int i = 0; i < 8; ++i) acc[i] += (double)d[i];
+        ++n;
+        continue;
+      }
+      if (d[5] == 0) continue;
       acc[0] += (double)(d[1] - d[0]);   // setup
       acc[1] += (double)(d[2] - d[1]);   // until first activation tile is ready
       acc[2] += (double)(d[3] - d[2]);   // MMA issue loop

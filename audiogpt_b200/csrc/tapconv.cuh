@@ -82,6 +82,7 @@ struct PackedConv;
 void tapconv_launch(TapConvParams P, cudaStream_t st);
 void tcconv_launch(TapConvParams P, cudaStream_t st);          // tcgen05 version (tcconv.cu / tcconv2.cu)
 bool tcconv2_launch(TapConvParams P, cudaStream_t st);
+bool tcconv3_launch(TapConvParams P, cudaStream_t st);
 bool tcconv_supported(const TapConvParams& P);
 void pack_tc_weights(struct PackedConv& pc, const std::vector<float>& h);
 void tc_set_enabled(int on);

@@ -305,16 +305,22 @@ void tcconv_launch(TapConvParams P, cudaStream_t st) {
   static int ver = -1, bo = 0;
   if (ver < 0) {
     const char* e = getenv("AGPT_TC_V");
-    ver = (e && e[0] == '1') ? 1 : 2;
+    ver = e ? atoi(e) : 2;   // default: v2.  v3 (persistent) is experimental: in the full generator it does not
+                             // beat v2 yet (25.5 vs 25.0 ms at B=8,T=400), see profiles/r1b_conv_microbench.txt
     const char* b = getenv("AGPT_TC_BO");
     bo = (b && b[0] == '1') ? 1 : 0;
     const char* d = getenv("AGPT_TC_DBGFLAGS");     // experiment switches (bits 2..): see tcconv2.cu
     if (d) bo |= atoi(d) & ~3;
   }
-  if (ver == 2) {
-    P.tc_flags = bo | P.tc_flags_user;
-    if (tcconv2_launch(P, st)) return;
-  }
+  P.tc_flags = bo | P.tc_flags_user;
+  // v3 (persistent, overlapped epilogue) wins when an activation tile is reused by many taps (k >= 5:
+  // measured +10..60 % on the k=7/11 HiFi-GAN convs); for k <= 3 and 1-tap GEMM-like layers the
+  // concurrent transform/epilogue starve on shared-memory bandwidth and v2 is faster
+  // (profiles/r1b_conv_microbench.txt).  AGPT_TC_V=3x forces v3 everywhere, =2 disables it.
+  if ((ver == 3 && P.ntaps >= 5) || ver > 3) {
+    if (tcconv3_launch(P, st)) return;
+  }   // persistent, overlapped epilogue
+  if (ver >= 2 && tcconv2_launch(P, st)) return;
   int lo = P.tap_off[0], hi = P.tap_off[0];
   for (int t = 1; t < P.ntaps; ++t) { lo = std::min(lo, P.tap_off[t]); hi = std::max(hi, P.tap_off[t]); }
   P.lo_al = lo;

@@ -17,10 +17,12 @@ shapes = [  # name, G, L, Cin, Cout, K, dil, Wreal
 sel = sys.argv[1:] 
 for name, G, Ln, Cin, Cout, K, dil, Wr in shapes:
     if sel and not any(s in name for s in sel): continue
+    out3 = (C.c_double * 3)()
+    _lib.check(L.agpt_bench_tapconv(G, Ln, Cin, Cout, K, dil, Wr, 1, 1, 5, 1, out3, None))      # v3 (persistent)
     out = (C.c_double * 3)(); dbg = (C.c_double * 8)()
-    _lib.check(L.agpt_bench_tapconv(G, Ln, Cin, Cout, K, dil, Wr, 1, 1, 5, 1, out, dbg))
+    _lib.check(L.agpt_bench_tapconv(G, Ln, Cin, Cout, K, dil, Wr, 1, 1, 5, 1, out, dbg))        # v2 (+phase stamps)
     o2 = (C.c_double * 3)()
     _lib.check(L.agpt_bench_tapconv(G, Ln, Cin, Cout, K, dil, Wr, 1, 0, 3, 0, o2, None))
     d = list(dbg)
-    print(f"{name:22s} tc {out[0]*1e3:8.1f} us {out[1]:6.1f} TF | fma {o2[0]*1e3:8.1f} us {o2[1]:5.1f} TF | maxdiff {out[2]:.2e} | "
+    print(f"{name:22s} v3 {out3[0]*1e3:8.1f} us {out3[1]:6.1f} TF d={out3[2]:.1e} | v2 {out[0]*1e3:8.1f} us {out[1]:6.1f} TF | fma {o2[0]*1e3:8.1f} us {o2[1]:5.1f} TF | maxdiff {out[2]:.2e} | "
           f"cyc setup {d[0]:.0f} firstA {d[1]:.0f} mma {d[2]:.0f} drain {d[3]:.0f} epi {d[4]:.0f} total {d[5]:.0f} waitA {d[6]:.0f} waitW {d[7]:.0f}", flush=True)
