@@ -10,37 +10,47 @@
 namespace agpt {
 
 // ------------------------------------------------------------------ GroupNorm
-// pass 1: per (n, split, channel) partial sum / sumsq in double
-__global__ void gn_partial_kernel(const float* __restrict__ x, double* __restrict__ part, int HW, int C, int S) {
+// pass 1: per (n, row-split, group) partial sum / sum of squares, accumulated in double
+// (per-thread channel sums -> shared-memory per-group reduction); grid (S, N)
+constexpr int GN_MAX_SPLIT = 32;
+__global__ void gn_partial_kernel(const float* __restrict__ x, double* __restrict__ part, int HW, int C, int S, int G) {
+  __shared__ double sg[64][2];
   const int n = blockIdx.y, s = blockIdx.x;
   const int r0 = (int)((long)HW * s / S), r1 = (int)((long)HW * (s + 1) / S);
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) { sg[g][0] = 0.0; sg[g][1] = 0.0; }
+  __syncthreads();
   const float* xb = x + (long)n * HW * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     double a = 0.0, b = 0.0;
     for (int r = r0; r < r1; ++r) {
-      const double v = (double)xb[(long)r * C + c];
+      const double v = (double)__ldg(xb + (long)r * C + c);
       a += v; b += v * v;
     }
-    double* o = part + (((long)n * S + s) * C + c) * 2;
-    o[0] = a; o[1] = b;
+    atomicAdd(&sg[c / cpg][0], a);
+    atomicAdd(&sg[c / cpg][1], b);
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double* o = part + (((long)n * S + s) * G + g) * 2;
+    o[0] = sg[g][0]; o[1] = sg[g][1];
   }
 }
 
-// pass 2: finalize (mean, rstd) per group from the partials, normalise a tile of rows
+// pass 2: every CTA folds the S x G partials of its sample (tiny) and normalises a slab of rows,
+// 128-bit loads/stores along the channel axis
 __global__ void gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ part,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 float* __restrict__ y, int HW, int C, int S, int G, float eps, int silu, int rows_per_cta) {
-  extern __shared__ float sm[];  // mean[G], rstd[G]
-  float* mean = sm; float* rstd = sm + G;
+  __shared__ float mean[64], rstd[64];
   const int n = blockIdx.y;
   const int cpg = C / G;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     double a = 0.0, b = 0.0;
-    for (int s = 0; s < S; ++s)
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        const double* p = part + (((long)n * S + s) * C + c) * 2;
-        a += p[0]; b += p[1];
-      }
+    for (int s = 0; s < S; ++s) {
+      const double* p = part + (((long)n * S + s) * G + g) * 2;
+      a += p[0]; b += p[1];
+    }
     const double cnt = (double)HW * cpg;
     const double m = a / cnt;
     double var = b / cnt - m * m;
@@ -52,27 +62,38 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, const double* __res
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
   const float* xb = x + (long)n * HW * C;
   float* yb = y + (long)n * HW * C;
-  const int total = (r1 - r0) * C;
+  const int c4n = C >> 2;
+  const int total = (r1 - r0) * c4n;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int r = r0 + i / C, c = i % C, g = c / cpg;
-    float v = (xb[(long)r * C + c] - mean[g]) * rstd[g] * gamma[c] + beta[c];
-    if (silu) v = siluf_(v);
-    yb[(long)r * C + c] = v;
+    const int r = r0 + i / c4n, c = (i % c4n) << 2;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (long)r * C + c));
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const int g0 = c / cpg, g1 = (c + 1) / cpg, g2 = (c + 2) / cpg, g3 = (c + 3) / cpg;
+    float4 o;
+    o.x = (v.x - mean[g0]) * rstd[g0] * ga.x + be.x;
+    o.y = (v.y - mean[g1]) * rstd[g1] * ga.y + be.y;
+    o.z = (v.z - mean[g2]) * rstd[g2] * ga.z + be.z;
+    o.w = (v.w - mean[g3]) * rstd[g3] * ga.w + be.w;
+    if (silu) { o.x = siluf_(o.x); o.y = siluf_(o.y); o.z = siluf_(o.z); o.w = siluf_(o.w); }
+    *reinterpret_cast<float4*>(yb + (long)r * C + c) = o;
   }
 }
 
 void groupnorm(const float* x, float* y, const float* gamma, const float* beta, int N, int HW, int C, int G,
                float eps, bool silu, double* scratch, cudaStream_t st) {
-  AGPT_CHECK(C % G == 0, "GroupNorm channels not divisible by groups");
-  const int S = std::max(1, std::min(16, HW / 32));
-  gn_partial_kernel<<<dim3(S, N), 256, 0, st>>>(x, scratch, HW, C, S);
-  const int rows_per_cta = 16;
-  gn_apply_kernel<<<dim3(cdiv(HW, rows_per_cta), N), 256, 2 * G * sizeof(float), st>>>(
+  AGPT_CHECK(C % G == 0 && G <= 64 && C % 4 == 0, "GroupNorm: channels must be divisible by groups (<= 64) and by 4");
+  const int S = std::max(1, std::min(GN_MAX_SPLIT, HW / 8));
+  gn_partial_kernel<<<dim3(S, N), 256, 0, st>>>(x, scratch, HW, C, S, G);
+  // ~2 waves of CTAs over 148 SMs
+  const int target_ctas = std::max(1, 296 / N);
+  const int rows_per_cta = std::max(1, cdiv(HW, target_ctas));
+  gn_apply_kernel<<<dim3(cdiv(HW, rows_per_cta), N), 256, 0, st>>>(
       x, scratch, gamma, beta, y, HW, C, S, G, eps, silu ? 1 : 0, rows_per_cta);
   count_launch(2);
   AGPT_CUDA(cudaGetLastError());
 }
-size_t groupnorm_scratch_doubles(int N, int C) { return (size_t)N * 16 * C * 2; }
+size_t groupnorm_scratch_doubles(int N, int C) { (void)C; return (size_t)N * GN_MAX_SPLIT * 64 * 2; }
 
 // ------------------------------------------------------------------ LayerNorm (one warp per row)
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
