@@ -44,6 +44,7 @@ int agpt_profile_collect(double ms[4], double flops[4], double bytes[4], long lo
   return guarded([&] { profile_collect(ms, flops, bytes, launches); });
 }
 int agpt_set_tensor_cores(int on) { return guarded([&] { tc_set_enabled(on); }); }
+int agpt_set_tc_version(int v) { return guarded([&] { tc_set_version(v); }); }
 double agpt_fma_peak_tflops(void) {
   double v = -1.0;
   guarded([&] { v = fma_peak_tflops(); });

@@ -86,6 +86,7 @@ bool tcconv3_launch(TapConvParams P, cudaStream_t st);
 bool tcconv_supported(const TapConvParams& P);
 void pack_tc_weights(struct PackedConv& pc, const std::vector<float>& h);
 void tc_set_enabled(int on);
+void tc_set_version(int v);
 bool tc_enabled();
 void profile_enable(int on);
 void profile_collect(double* ms, double* flops, double* bytes, long long* launches);

@@ -284,6 +284,8 @@ void pack_tc_weights(PackedConv& pc, const std::vector<float>& h) {
   pc.tc_chunks = nch;
 }
 
+static int g_tc_version = -1;  // -1: AGPT_TC_V or the default; 1 = per-tap tiles, 2 = shifted descriptors, 3/4 = persistent
+void tc_set_version(int v) { g_tc_version = v; }
 static int g_tc_enabled = -1;   // -1: read AGPT_TENSOR_CORES from the environment on first use
 void tc_set_enabled(int on) { g_tc_enabled = on != 0 ? 1 : 0; }
 bool tc_enabled() {
@@ -302,7 +304,8 @@ bool tcconv_supported(const TapConvParams& P) {
 }
 
 void tcconv_launch(TapConvParams P, cudaStream_t st) {
-  static int ver = -1, bo = 0;
+  static int bo = 0;
+  int& ver = g_tc_version;
   if (ver < 0) {
     const char* e = getenv("AGPT_TC_V");
     ver = e ? atoi(e) : 2;   // default: v2.  v3 (persistent) is experimental: in the full generator it does not

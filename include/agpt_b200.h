@@ -39,6 +39,9 @@ double agpt_fma_peak_tflops(void);
 /* 1 (default): contractions run on tcgen05 tensor cores with 3xTF32 error compensation;
  * 0: fp32-FMA kernels only (bit-for-bit the round-1 numerics).                            */
 int agpt_set_tensor_cores(int on);
+/* tcgen05 kernel generation: 1 = per-tap operand tiles, 2 = shifted-descriptor taps (default),
+ * 3 = persistent for k >= 5, 4 = persistent everywhere (experimental); -1 = environment/default. */
+int agpt_set_tc_version(int v);
 /* Micro-benchmark of one tapconv layer (random data): out3 = {ms per launch, algorithmic TFLOP/s,
  * max |tcgen05 - fp32 FMA| when check != 0}; dbg8 (tcgen05 only) = average per-CTA phase cycles
  * {setup, first activation tile, MMA issue loop, drain, epilogue, total, wait-on-activations,

@@ -55,6 +55,22 @@ def test_product_never_imports_oracle():
     assert not bad, bad
 
 
+def test_install_aliases_reference_module_names():
+    """Without the reference tree on sys.path, install() registers the drop-ins under the reference's
+    module names, so `from modules.hifigan.hifigan import HifiGanGenerator` resolves to ours."""
+    code = ("import sys; sys.path.insert(0, %r); import audiogpt_b200 as a; p = a.install(); "
+            "from modules.hifigan.hifigan import HifiGanGenerator as H; "
+            "from ldm.modules.diffusionmodules.openaimodel import UNetModel as U; "
+            "from ldm.models.diffusion.ddim import DDIMSampler as D; "
+            "from modules.diff.shallow_diffusion_tts import GaussianDiffusion as G; "
+            "assert H.__module__.startswith('audiogpt_b200') and U.__module__.startswith('audiogpt_b200'); "
+            "assert D.__module__.startswith('audiogpt_b200') and G.__module__.startswith('audiogpt_b200'); "
+            "print(len(p))") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip() == "6"
+
+
 def test_param_tables_match_survey_counts():
     n = lambda shapes: sum(int(np.prod(s)) for s in shapes.values())
     assert n(specs.hifigan_param_shapes(specs.HIFIGAN_V1)) == 13_926_017   # 13.93 M (SURVEY 8a)
