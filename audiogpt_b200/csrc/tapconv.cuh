@@ -54,6 +54,7 @@ struct TapConvParams {
   int epi; const float* res; long res_gstride; int res_pitch; float scale; int accumulate;
   const float* evec; int evec_gstride;
   float* out2; long out2_gstride; int out2_pitch; int csplit;
+  const float* w_tc256;   // optional BN=256 image (layers with Cout % 256 == 0)
   const float* w_tc; int tc_bn, tc_chunks, tc_na, tc_nw, tc_nr, tc_flags, tc_flags_user;
   long long* dbg;      // optional per-CTA phase timestamps (tc_flags & 2)   // tensor-core weight image (tcconv.cu); tc_bn == 0 => FMA only
   float flops_scale;   // useful fraction of the MACs (zero-padded polyphase taps); 0 => 1
@@ -61,7 +62,7 @@ struct TapConvParams {
 
 // ---------------------------------------------------------------- host side
 struct PackedConv {
-  DevBuf w, b, w_tc;
+  DevBuf w, b, w_tc, w_tc256;
   int tc_bn = 0, tc_chunks = 0;
   int Cin = 0, cin_pad = 0, Cout = 0, cout_pad = 0, ntaps = 0;
   int tap_off_1d[kMaxTaps] = {0};   // for 1-D convs: row offsets; 2-D convs derive offsets from W at launch
@@ -111,7 +112,7 @@ inline TapConvParams tapconv_params(const PackedConv& pc, int G, int L, int Wrea
   }
   P.scale = 1.f;
   P.flops_scale = pc.useful;
-  P.w_tc = pc.w_tc.p; P.tc_bn = pc.tc_bn; P.tc_chunks = pc.tc_chunks;
+  P.w_tc = pc.w_tc.p; P.tc_bn = pc.tc_bn; P.tc_chunks = pc.tc_chunks; P.w_tc256 = pc.w_tc256.p;
   return P;
 }
 

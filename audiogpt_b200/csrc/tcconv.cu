@@ -251,8 +251,18 @@ static int tcgen_pick_bn(int cout) { return cout > 64 ? 128 : (cout > 32 ? 64 : 
 
 // Build the tensor-core weight image from the FMA-layout host array h[tap][cin_pad][cout_pad]:
 //   [co-tile][chunk][tap][hi | lo][BN rows (co) x 32 ci], each [BN][128 B] block in SWIZZLE_128B order.
+static void build_tc_image(const PackedConv& pc, const std::vector<float>& h, int BN, DevBuf& dst);
+
 void pack_tc_weights(PackedConv& pc, const std::vector<float>& h) {
-  const int BN = tcgen_pick_bn(pc.Cout);
+  build_tc_image(pc, h, tcgen_pick_bn(pc.Cout), pc.w_tc);
+  pc.tc_bn = tcgen_pick_bn(pc.Cout);
+  pc.tc_chunks = cdiv(pc.Cin, TC_KCH);
+  // wide layers also get a BN=256 image: half the activation-operand bytes per FLOP (tcconv2 picks it
+  // when the tile fits the shared-memory budget)
+  if (pc.Cout % 256 == 0) build_tc_image(pc, h, 256, pc.w_tc256);
+}
+
+static void build_tc_image(const PackedConv& pc, const std::vector<float>& h, int BN, DevBuf& dst) {
   const int nct = cdiv(pc.Cout, BN), nch = cdiv(pc.Cin, TC_KCH), nt = pc.ntaps;
   const size_t blk = (size_t)BN * 32;  // floats per hi (or lo) block
   std::vector<float> img((size_t)nct * nch * nt * 2 * blk, 0.f);
@@ -279,9 +289,7 @@ void pack_tc_weights(PackedConv& pc, const std::vector<float>& h) {
           }
         }
       }
-  pc.w_tc.upload(img);
-  pc.tc_bn = BN;
-  pc.tc_chunks = nch;
+  dst.upload(img);
 }
 
 static int g_tc_version = -1;  // -1: AGPT_TC_V or the default; 1 = per-tap tiles, 2 = shifted descriptors, 3/4 = persistent

@@ -317,14 +317,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
 
 }  // namespace
 
-// returns false when the shape does not fit the shared-memory budget (caller falls back to v1)
-bool tcconv2_launch(TapConvParams P, cudaStream_t st) {
+// Try one tile width; returns false when it does not fit the shared-memory budget.
+static bool tcconv2_try(TapConvParams P, int BN, cudaStream_t st) {
   int lo = P.tap_off[0], hi = P.tap_off[0];
   for (int t = 1; t < P.ntaps; ++t) { lo = std::min(lo, P.tap_off[t]); hi = std::max(hi, P.tap_off[t]); }
   P.lo_al = lo;
   const int RRA = round_up(TC_ROWS + (hi - lo), 8);
   P.R = RRA;
-  const int BN = P.tc_bn;
+  P.tc_bn = BN;
   const long avail = (long)kMaxDyn - 1024 /*align*/ - (RRA * 4 + TC_ROWS * 4 + 512) /*row tables + barriers*/;
   const long abytes = 2L * RRA * 128, wbytes = 2L * BN * 128;
   const long rbytes = (long)RRA * 128;
@@ -334,8 +334,8 @@ bool tcconv2_launch(TapConvParams P, cudaStream_t st) {
   int NR = (P.ntaps == 1 && P.tc_chunks > 1) ? 2 : 1;
   auto fits = [&](int na, int nr, int nw) { return na * abytes + nr * rbytes + nw * wbytes <= avail; };
   // the epilogue stages through the first 32 KB of the operand buffers
-  if (!fits(NA, NR, 2) && NR == 2) NR = 1;
   if (!fits(NA, NR, 2) && NA == 3) NA = 2;
+  if (!fits(NA, NR, 2) && NR == 2) NR = 1;
   if (!fits(NA, NR, 2) && (long)RRA * 128 >= 32768) NA = 1;
   if (!fits(NA, NR, 2)) return false;
   int NW = (int)std::min<long>(MAX_NW, (avail - NA * abytes - NR * rbytes) / wbytes);
@@ -356,15 +356,36 @@ bool tcconv2_launch(TapConvParams P, cudaStream_t st) {
   AGPT_CUDA(cudaGetDevice(&dev));
   static bool attr_done_dev[64] = {false};
   if (!attr_done_dev[dev & 63]) {
+    AGPT_CUDA(cudaFuncSetAttribute(tcconv2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
     AGPT_CUDA(cudaFuncSetAttribute(tcconv2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
     AGPT_CUDA(cudaFuncSetAttribute(tcconv2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
     AGPT_CUDA(cudaFuncSetAttribute(tcconv2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
     attr_done_dev[dev & 63] = true;
   }
-  if (BN == 128) tcconv2_kernel<128><<<grid, TC_THREADS, smem, st>>>(P);
+  if (BN == 256) tcconv2_kernel<256><<<grid, TC_THREADS, smem, st>>>(P);
+  else if (BN == 128) tcconv2_kernel<128><<<grid, TC_THREADS, smem, st>>>(P);
   else if (BN == 64) tcconv2_kernel<64><<<grid, TC_THREADS, smem, st>>>(P);
   else tcconv2_kernel<32><<<grid, TC_THREADS, smem, st>>>(P);
   return true;
+}
+
+// returns false when the shape does not fit the shared-memory budget (caller falls back to v1)
+bool tcconv2_launch(TapConvParams P, cudaStream_t st) {
+  static int allow256 = -1;
+  if (allow256 < 0) { const char* e = getenv("AGPT_TC_BN256"); allow256 = (e && e[0] == '0') ? 0 : 1; }
+  if (allow256 && P.w_tc256) {
+    // BN=256 halves the activation-operand bytes per FLOP, but only pays when the grid still fills the
+    // machine (>= ~1 wave of CTAs)
+    const int Wv = P.Wreal > 0 ? P.Wreal + 1 : 0;
+    const int Lv = Wv ? (P.L / P.Wreal) * Wv : P.L;
+    const long ctas256 = (long)cdiv(Lv, TC_ROWS) * (P.Cout / 256) * P.G;
+    if (ctas256 >= 120) {
+      TapConvParams Q = P;
+      Q.w_tc = P.w_tc256;
+      if (tcconv2_try(Q, 256, st)) return true;
+    }
+  }
+  return tcconv2_try(P, P.tc_bn, st);
 }
 
 }  // namespace agpt
