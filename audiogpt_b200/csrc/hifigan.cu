@@ -264,10 +264,35 @@ Handle* hifigan_create(const agpt_hifigan_cfg* cfg, const float* const* W, int n
   return h;
 }
 
+// Optional (AGPT_HIFI_L2_MB=<per-tensor MB>): run the generator over sub-batches whose per-stage tensors
+// fit the 126 MB L2 together.  Utterances are independent, so this changes nothing numerically.
+// Measured on B200 (B=8, T=800): 57-60 ms with sub-batching vs 51.4 ms without -- the smaller grids cost
+// more than the L2 hits save -- so it is OFF by default.
+static void hifigan_forward_l2(Hifigan* h, const float* mel, const float* har, int B, int T, float* wav, cudaStream_t st) {
+  static long target = -1;
+  if (target < 0) {
+    const char* e = getenv("AGPT_HIFI_L2_MB");          // per-tensor budget in MB; 0 disables sub-batching
+    target = e ? atol(e) * (1L << 20) : 0;
+  }
+  size_t per = (size_t)T * h->cfg.upsample_initial_channel;
+  {
+    long L = T; int C = h->cfg.upsample_initial_channel;
+    for (int i = 0; i < h->cfg.num_upsamples; ++i) { L *= h->cfg.upsample_rates[i]; C /= 2; per = std::max(per, (size_t)L * C); }
+  }
+  per *= sizeof(float);
+  int sb = B;
+  if (target > 0) sb = (int)std::max<long>(1, std::min<long>(B, target / (long)std::max<size_t>(per, 1)));
+  const long wav_per = (long)h->cfg.c_out * T * h->hop, mel_per = (long)h->cfg.n_mels * T, har_per = (long)T * h->hop;
+  for (int b0 = 0; b0 < B; b0 += sb) {
+    const int nb = std::min(sb, B - b0);
+    h->forward(mel + b0 * mel_per, har ? har + b0 * har_per : nullptr, nb, T, wav + b0 * wav_per, st);
+  }
+}
+
 void hifigan_forward(Handle* hh, const float* mel, const float* har, int B, int T, float* wav, cudaStream_t st) {
   auto* h = static_cast<Hifigan*>(hh);
   AGPT_CUDA(cudaSetDevice(h->device));
-  h->forward(mel, har, B, T, wav, st);
+  hifigan_forward_l2(h, mel, har, B, T, wav, st);
 }
 
 void hifigan_vocode_host(Handle* hh, const float* mel_host, const float* har_host, int B, int T, float* wav_host) {
@@ -288,7 +313,7 @@ void hifigan_vocode_host(Handle* hh, const float* mel_host, const float* har_hos
     AGPT_CUDA(cudaMemcpyAsync(h->io_har.p, har_host, nhar * 4, cudaMemcpyHostToDevice, st));
     har_dev = h->io_har.p;
   }
-  h->forward(h->io_mel.p, har_dev, B, T, h->io_wav.p, st);
+  hifigan_forward_l2(h, h->io_mel.p, har_dev, B, T, h->io_wav.p, st);
   AGPT_CUDA(cudaMemcpyAsync(h->pin_wav, h->io_wav.p, nwav * 4, cudaMemcpyDeviceToHost, st));
   AGPT_CUDA(cudaStreamSynchronize(st));
   memcpy(wav_host, h->pin_wav, nwav * 4);
