@@ -55,7 +55,7 @@ struct TapConvParams {
   const float* evec; int evec_gstride;
   float* out2; long out2_gstride; int out2_pitch; int csplit;
   const float* w_tc256;   // optional BN=256 image (layers with Cout % 256 == 0)
-  const float* w_tc; int tc_bn, tc_chunks, tc_na, tc_nw, tc_nr, tc_flags, tc_flags_user;
+  const float* w_tc; int tc_bn, tc_chunks, tc_na, tc_nw, tc_nr, tc_nwk, tc_flags, tc_flags_user;
   long long* dbg;      // optional per-CTA phase timestamps (tc_flags & 2)   // tensor-core weight image (tcconv.cu); tc_bn == 0 => FMA only
   float flops_scale;   // useful fraction of the MACs (zero-padded polyphase taps); 0 => 1
 };

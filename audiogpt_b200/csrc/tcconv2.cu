@@ -55,8 +55,11 @@ __device__ __forceinline__ float4 pro_apply(const TapConvParams& P, float4 v, bo
 }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
-template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_constant__ TapConvParams P) {
+constexpr int V2_MAXWORKERS = 256;   // 8 worker warps (0-3 and 6-9): transform, then epilogue (4 for tiny tiles)
+constexpr int V2_THREADS = 320;   // + warp 4 (MMA issuer) + warp 5 (weight producer)
+
+template <int BN, int V2_WORKERS>
+__global__ void __launch_bounds__(V2_WORKERS == 256 ? V2_THREADS : 192, 1) tcconv2_kernel(const __grid_constant__ TapConvParams P) {
   extern __shared__ uint8_t smem_raw_[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
   const int RRA = P.R, NA = P.tc_na, NW = P.tc_nw, NR = P.tc_nr;
@@ -74,6 +77,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
   int* rowp = reinterpret_cast<int*>(smem + S.rowp);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_worker = warp < 4 || warp >= 6;
+  const int xt = warp < 4 ? tid : tid - 64;      // worker thread index 0..255
+  const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
+  const int sub = warp < 4 ? 0 : 1;               // which of the two worker warps of that quadrant
   const int g = blockIdx.z, co0 = blockIdx.y * BN, q0 = blockIdx.x * TC_ROWS;
   const int Wv = P.Wreal > 0 ? P.Wreal + 1 : 0;
   const int Lv = Wv ? (P.L / P.Wreal) * Wv : P.L;
@@ -84,7 +91,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
   if (dbg_on && tid == 0) dbg[0] = clock64();
 
   if (tid == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], V2_WORKERS); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
@@ -94,8 +101,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
                  ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)(BN < 32 ? 32 : BN)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp < 4) {
-    for (int i = tid; i < RRA; i += 128) {
+  if (is_worker) {
+    for (int i = xt; i < RRA; i += V2_WORKERS) {
       const int q = q0 + lo + i;
       int a = -1;
       if (q >= 0 && q < Lv) {
@@ -108,8 +115,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
       }
       rowinfo[i] = a;
     }
-    {  // output row -> real position (or -1)
-      const int q = q0 + tid;
+    if (xt < TC_ROWS) {  // output row -> real position (or -1)
+      const int q = q0 + xt;
       int p = -1;
       if (q < Lv) {
         if (Wv) {
@@ -119,7 +126,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
           p = q;
         }
       }
-      rowp[tid] = p;
+      rowp[xt] = p;
     }
   }
   tc_fence_before();
@@ -128,14 +135,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   if (dbg_on && tid == 0) dbg[1] = clock64();
 
-  if (warp < 4) {
-    // =========================== transform warps ===========================
+  if (is_worker) {
+    // =========================== worker warps: transform ===========================
     const float* __restrict__ ing = P.in + g * P.in_gstride;
     const float* pvg = (P.pro == PRO_ADDVEC) ? (P.pvec + (long)g * P.pvec_gstride) : nullptr;
     const int items = RRA * 8;
     auto issue_raw = [&](int c, int rb) {
       uint8_t* dst = smem + S.raw[rb];
-      for (int idx = tid; idx < items; idx += 128) {
+      for (int idx = xt; idx < items; idx += V2_WORKERS) {
         const int row = idx >> 3, j = idx & 7;
         const int ch = c * TC_KCH + 4 * j;
         const int a = rowinfo[row];
@@ -155,7 +162,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
       if (P.epi == EPI_ACC && P.accumulate) { pf1 = P.out; gs1 = P.out_gstride; pitch1 = P.out_pitch; }
       if (P.epi == EPI_DIFFOUT) { pf0 = P.out; gs0 = P.out_gstride; pitch0 = P.out_pitch; }
       const int lines = (BN * 4) / 128 > 0 ? (BN * 4) / 128 : 1;     // 128-byte lines per output row
-      for (int idx = tid; idx < TC_ROWS * lines; idx += 128) {
+      for (int idx = xt; idx < TC_ROWS * lines; idx += V2_WORKERS) {
         const int p = rowp[idx / lines];
         const int co = co0 + (idx % lines) * 32;
         if (p >= 0 && co < P.Cout) {
@@ -170,13 +177,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
       // raw(c) landed?  (with NR == 2 one younger group -- raw(c+1) -- may still be in flight)
       if (NR == 2 && c + 1 < nchunks) asm volatile("cp.async.wait_group 1;" ::: "memory");
       else cp_async_wait_all_();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, V2_WORKERS);
       if (n >= 1) mbar_wait(&a_empty[buf], (uint32_t)((n - 1) & 1));
       uint8_t* ahi = smem + S.a_hi[buf];
       uint8_t* alo = smem + S.a_lo[buf];
       const uint8_t* rawb = smem + S.raw[rb];
 #pragma unroll 2
-      for (int idx = tid; idx < items; idx += 128) {
+      for (int idx = xt; idx < items; idx += V2_WORKERS) {
         const int row = idx >> 3, j = idx & 7;
         const uint32_t o = sw128(row, j);
         const float4 v = *reinterpret_cast<const float4*>(rawb + o);
@@ -192,23 +199,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
       // refill the raw buffer just consumed
       const int cn = c + NR;
       if (cn < nchunks) {
-        named_bar_sync(1, 128);          // everyone finished reading raw[rb]
+        named_bar_sync(1, V2_WORKERS);          // everyone finished reading raw[rb]
         issue_raw(cn, rb);
       }
     }
-    // =========================== epilogue ===========================
+    // =========================== worker warps: epilogue ===========================
     // TMEM -> registers -> swizzled staging block [128 rows][32 cols] in shared memory (the operand
     // buffers are free now) -> coalesced (row, 16-byte chunk) items through the fused epilogue.
-    // 8 (row, 16-byte chunk) items per thread and 32-column block.  The global READS of a block
-    // (residual / old accumulator) are issued one block ahead -- for block 0 even before the
-    // accumulator is complete -- so their latency overlaps the tail of the main loop.
+    // Each TMEM lane quadrant has two worker warps; they alternate over the 32-column blocks.  All
+    // 256 workers share the coalesced pass (4 items each); the global READS of a block (residual /
+    // old accumulator) are issued one block ahead -- for block 0 before the accumulator is complete.
     EpiPre pre[8];
     int pp[8];
+    constexpr int nitem = (TC_ROWS * 8) / V2_WORKERS;   // 4 or 8 items per worker and block
     auto load_block = [&](int cb) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int idx = tid + i * 128;
-        pp[i] = rowp[idx >> 3];
+        const int idx = xt + i * V2_WORKERS;
+        pp[i] = (i < nitem) ? rowp[idx >> 3] : -1;
         if (P.tc_flags & 4) { pre[i].a = make_float4(0.f, 0.f, 0.f, 0.f); pre[i].b = pre[i].a; continue; }   // experiment: no global reads
         if (pp[i] >= 0) epi_load(P, g, pp[i], co0 + cb + 4 * (idx & 7), pre[i]);
       }
@@ -218,31 +226,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
     tc_fence_after();
     if (dbg_on && tid == 0) dbg[4] = clock64();
     uint8_t* stg0 = smem + S.a_hi[0];            // 2 x 16 KB inside the first operand buffers (>= 32 KB)
+    const int myrow = quad * 32 + lane;
 #pragma unroll 1
     for (int cb = 0, blk = 0; cb < BN; cb += 32, ++blk) {
-      uint32_t rg[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(rg[0]), "=r"(rg[1]), "=r"(rg[2]), "=r"(rg[3]), "=r"(rg[4]), "=r"(rg[5]), "=r"(rg[6]), "=r"(rg[7]),
-            "=r"(rg[8]), "=r"(rg[9]), "=r"(rg[10]), "=r"(rg[11]), "=r"(rg[12]), "=r"(rg[13]), "=r"(rg[14]), "=r"(rg[15]),
-            "=r"(rg[16]), "=r"(rg[17]), "=r"(rg[18]), "=r"(rg[19]), "=r"(rg[20]), "=r"(rg[21]), "=r"(rg[22]), "=r"(rg[23]),
-            "=r"(rg[24]), "=r"(rg[25]), "=r"(rg[26]), "=r"(rg[27]), "=r"(rg[28]), "=r"(rg[29]), "=r"(rg[30]), "=r"(rg[31])
-          : "r"(taddr) : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       uint8_t* stg = stg0 + (blk & 1) * (TC_ROWS * 128);
+      if (V2_WORKERS == 128 || sub == (blk & 1)) {
+        uint32_t rg[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)cb;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(rg[0]), "=r"(rg[1]), "=r"(rg[2]), "=r"(rg[3]), "=r"(rg[4]), "=r"(rg[5]), "=r"(rg[6]), "=r"(rg[7]),
+              "=r"(rg[8]), "=r"(rg[9]), "=r"(rg[10]), "=r"(rg[11]), "=r"(rg[12]), "=r"(rg[13]), "=r"(rg[14]), "=r"(rg[15]),
+              "=r"(rg[16]), "=r"(rg[17]), "=r"(rg[18]), "=r"(rg[19]), "=r"(rg[20]), "=r"(rg[21]), "=r"(rg[22]), "=r"(rg[23]),
+              "=r"(rg[24]), "=r"(rg[25]), "=r"(rg[26]), "=r"(rg[27]), "=r"(rg[28]), "=r"(rg[29]), "=r"(rg[30]), "=r"(rg[31])
+            : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int qd = 0; qd < 8; ++qd)
-        *reinterpret_cast<float4*>(stg + sw128(tid, qd)) =
-            make_float4(__uint_as_float(rg[4 * qd]), __uint_as_float(rg[4 * qd + 1]),
-                        __uint_as_float(rg[4 * qd + 2]), __uint_as_float(rg[4 * qd + 3]));
-      named_bar_sync(1, 128);
+        for (int qd = 0; qd < 8; ++qd)
+          *reinterpret_cast<float4*>(stg + sw128(myrow, qd)) =
+              make_float4(__uint_as_float(rg[4 * qd]), __uint_as_float(rg[4 * qd + 1]),
+                          __uint_as_float(rg[4 * qd + 2]), __uint_as_float(rg[4 * qd + 3]));
+      }
+      named_bar_sync(1, V2_WORKERS);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int idx = tid + i * 128;
-        const int row = idx >> 3, j = idx & 7;
+        const int idx = xt + i * V2_WORKERS;
+        const int row = (idx >> 3) & (TC_ROWS - 1), j = idx & 7;   // pp[i] < 0 for i >= nitem
         if (pp[i] >= 0 && !((P.tc_flags & 8) && (row & 63) != 0))   // experiment bit 8: store 2 rows only
           epi_store(P, g, pp[i], co0 + cb + 4 * j, *reinterpret_cast<const float4*>(stg + sw128(row, j)), pre[i]);
       }
@@ -294,7 +305,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv2_kernel(const __grid_con
       umma_commit(acc_full);
       if (dbg_on) { dbg[3] = clock64(); dbg[6] = dbg_wa; dbg[7] = dbg_ww; }
     }
-  } else {
+  } else if (warp == 5) {
     // =========================== weight producer ===========================
     if (lane == 0) {
       const uint32_t bytes = 2u * BN * 128u;
@@ -345,6 +356,9 @@ static bool tcconv2_try(TapConvParams P, int BN, cudaStream_t st) {
   }
   NW = std::max(2, std::min(NW, std::max(2, iters)));
   P.tc_na = NA; P.tc_nw = NW; P.tc_nr = NR;
+  // tiny tiles (BN=32, <= 3 taps, one chunk) are launch/teardown bound: 4 worker warps are enough
+  P.tc_nwk = (BN <= 32 && iters <= 4) ? 128 : 256;
+  const int nthreads = P.tc_nwk == 128 ? 192 : V2_THREADS;
   Tc2Smem S;
   tc2_layout(S, BN, RRA, NA, NW, NR);
   const size_t smem = (size_t)S.total + 1024;
@@ -356,16 +370,18 @@ static bool tcconv2_try(TapConvParams P, int BN, cudaStream_t st) {
   AGPT_CUDA(cudaGetDevice(&dev));
   static bool attr_done_dev[64] = {false};
   if (!attr_done_dev[dev & 63]) {
-    AGPT_CUDA(cudaFuncSetAttribute(tcconv2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
-    AGPT_CUDA(cudaFuncSetAttribute(tcconv2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
-    AGPT_CUDA(cudaFuncSetAttribute(tcconv2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
-    AGPT_CUDA(cudaFuncSetAttribute(tcconv2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
+    AGPT_CUDA(cudaFuncSetAttribute(tcconv2_kernel<256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
+    AGPT_CUDA(cudaFuncSetAttribute(tcconv2_kernel<128, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
+    AGPT_CUDA(cudaFuncSetAttribute(tcconv2_kernel<64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
+    AGPT_CUDA(cudaFuncSetAttribute(tcconv2_kernel<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
+    AGPT_CUDA(cudaFuncSetAttribute(tcconv2_kernel<32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
     attr_done_dev[dev & 63] = true;
   }
-  if (BN == 256) tcconv2_kernel<256><<<grid, TC_THREADS, smem, st>>>(P);
-  else if (BN == 128) tcconv2_kernel<128><<<grid, TC_THREADS, smem, st>>>(P);
-  else if (BN == 64) tcconv2_kernel<64><<<grid, TC_THREADS, smem, st>>>(P);
-  else tcconv2_kernel<32><<<grid, TC_THREADS, smem, st>>>(P);
+  if (BN == 256) tcconv2_kernel<256, 256><<<grid, nthreads, smem, st>>>(P);
+  else if (BN == 128) tcconv2_kernel<128, 256><<<grid, nthreads, smem, st>>>(P);
+  else if (BN == 64) tcconv2_kernel<64, 256><<<grid, nthreads, smem, st>>>(P);
+  else if (P.tc_nwk == 128) tcconv2_kernel<32, 128><<<grid, nthreads, smem, st>>>(P);
+  else tcconv2_kernel<32, 256><<<grid, nthreads, smem, st>>>(P);
   return true;
 }
 
