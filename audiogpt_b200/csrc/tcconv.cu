@@ -260,6 +260,7 @@ void pack_tc_weights(PackedConv& pc, const std::vector<float>& h) {
   // wide layers also get a BN=256 image: half the activation-operand bytes per FLOP (tcconv2 picks it
   // when the tile fits the shared-memory budget)
   if (pc.Cout % 256 == 0) build_tc_image(pc, h, 256, pc.w_tc256);
+  pack_h_weights(pc, h);   // fp16 hi/lo image (tcconv5.cu)
 }
 
 static void build_tc_image(const PackedConv& pc, const std::vector<float>& h, int BN, DevBuf& dst) {
@@ -311,24 +312,34 @@ bool tcconv_supported(const TapConvParams& P) {
   return true;
 }
 
-void tcconv_launch(TapConvParams P, cudaStream_t st) {
-  static int bo = 0;
+static int g_tc_flags_env = 0;
+int tc_get_version() {
   int& ver = g_tc_version;
   if (ver < 0) {
     const char* e = getenv("AGPT_TC_V");
-    ver = e ? atoi(e) : 2;   // default: v2.  v3 (persistent) is experimental: in the full generator it does not
-                             // beat v2 yet (25.5 vs 25.0 ms at B=8,T=400), see profiles/r1b_conv_microbench.txt
-    const char* b = getenv("AGPT_TC_BO");
-    bo = (b && b[0] == '1') ? 1 : 0;
-    const char* d = getenv("AGPT_TC_DBGFLAGS");     // experiment switches (bits 2..): see tcconv2.cu
-    if (d) bo |= atoi(d) & ~3;
+    ver = e ? atoi(e) : 5;   // default: v5 (fp16 hi/lo operands); 2 = the tf32 hi/lo kernel; 3/4 = persistent tf32 (experimental)
   }
+  static bool env_done = false;
+  if (!env_done) {
+    env_done = true;
+    const char* b = getenv("AGPT_TC_BO");
+    g_tc_flags_env = (b && b[0] == '1') ? 1 : 0;
+    const char* d = getenv("AGPT_TC_DBGFLAGS");     // experiment switches (bits 2..): see tcconv2.cu
+    if (d) g_tc_flags_env |= atoi(d) & ~3;
+  }
+  return ver;
+}
+
+void tcconv_launch(TapConvParams P, cudaStream_t st) {
+  const int ver = tc_get_version();
+  const int bo = g_tc_flags_env;
   P.tc_flags = bo | P.tc_flags_user;
   // v3 (persistent, overlapped epilogue) wins when an activation tile is reused by many taps (k >= 5:
   // measured +10..60 % on the k=7/11 HiFi-GAN convs); for k <= 3 and 1-tap GEMM-like layers the
   // concurrent transform/epilogue starve on shared-memory bandwidth and v2 is faster
   // (profiles/r1b_conv_microbench.txt).  AGPT_TC_V=3x forces v3 everywhere, =2 disables it.
-  if ((ver == 3 && P.ntaps >= 5) || ver > 3) {
+  if (ver == 5 && tcconv5_launch(P, st)) return;
+  if ((ver == 3 && P.ntaps >= 5) || ver == 4) {
     if (tcconv3_launch(P, st)) return;
   }   // persistent, overlapped epilogue
   if (ver >= 2 && tcconv2_launch(P, st)) return;

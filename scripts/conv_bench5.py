@@ -1,0 +1,33 @@
+"""Dev probe: per-layer tapconv micro-benchmarks, fp16 hi/lo (v5) vs tf32 hi/lo (v2) vs fp32 FMA."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from audiogpt_b200 import _lib
+L = _lib.lib()
+torch.cuda.init(); torch.zeros(1).cuda()
+shapes = [  # name, G, L, Cin, Cout, K, dil, Wreal
+    ("hifi s0 k11", 8, 3200, 256, 256, 11, 1, 0), ("hifi s0 k3", 8, 3200, 256, 256, 3, 1, 0),
+    ("hifi s1 k3", 8, 25600, 128, 128, 3, 1, 0),
+    ("hifi s1 k11", 8, 25600, 128, 128, 11, 5, 0), ("hifi s2 k11", 8, 51200, 64, 64, 11, 1, 0),
+    ("hifi s2 k3", 8, 51200, 64, 64, 3, 1, 0),
+    ("hifi s3 k11", 8, 102400, 32, 32, 11, 1, 0), ("hifi s3 k3", 8, 102400, 32, 32, 3, 1, 0),
+    ("diffnet dil", 16, 400, 256, 512, 3, 1, 0), ("diffnet out1x1", 16, 400, 256, 512, 1, 1, 0),
+    ("unet lin 320", 1, 6240, 320, 320, 1, 1, 0), ("unet ff1", 1, 6240, 320, 2560, 1, 1, 0),
+    ("unet ff2", 1, 6240, 1280, 320, 1, 1, 0), ("unet conv 320", 8, 780, 320, 320, 3, 1, 78),
+    ("unet conv 640@5x39", 8, 195, 640, 640, 3, 1, 39), ("unet conv 1280->640", 8, 195, 1280, 640, 3, 1, 39),
+]
+sel = sys.argv[1:]
+for name, G, Ln, Cin, Cout, K, dil, Wr in shapes:
+    if sel and not any(s in name for s in sel): continue
+    res = {}
+    for ver in (5, 2):
+        _lib.check(L.agpt_set_tc_version(ver))
+        out = (C.c_double * 3)(); dbg = (C.c_double * 8)()
+        _lib.check(L.agpt_bench_tapconv(G, Ln, Cin, Cout, K, dil, Wr, 1, 1, 5, 1, out, dbg))
+        res[ver] = (list(out), list(dbg))
+    o2 = (C.c_double * 3)()
+    _lib.check(L.agpt_bench_tapconv(G, Ln, Cin, Cout, K, dil, Wr, 1, 0, 3, 0, o2, None))
+    o5, d = res[5]; ov2, dv2 = res[2]
+    print(f"{name:22s} v5 {o5[0]*1e3:8.1f} us {o5[1]:6.1f} TF d={o5[2]:.1e} | v2 {ov2[0]*1e3:8.1f} us {ov2[1]:6.1f} TF d={ov2[2]:.1e} | fma {o2[0]*1e3:8.1f} us | "
+          f"v5 cyc setup {d[0]:.0f} firstA {d[1]:.0f} mma {d[2]:.0f} drain {d[3]:.0f} epi {d[4]:.0f} total {d[5]:.0f} waitA {d[6]:.0f} waitW {d[7]:.0f} | v2 mma {dv2[2]:.0f} total {dv2[5]:.0f}", flush=True)
+_lib.check(L.agpt_set_tc_version(-1))

@@ -76,10 +76,11 @@ SHAPES = [  # G, L, Cin, Cout, K, dil, Wreal
     (2, 3000, 256, 256, 11, 5, 0), (2, 5000, 128, 128, 3, 3, 0), (2, 9000, 32, 32, 7, 1, 0),
     (3, 400, 256, 512, 3, 2, 0), (1, 777, 320, 320, 1, 1, 0), (2, 780, 320, 320, 3, 1, 78),
     (2, 195, 640, 640, 3, 1, 39), (1, 130, 1280, 320, 1, 1, 0), (2, 4, 64, 96, 3, 1, 0),
+    (2, 300, 80, 256, 7, 1, 0), (1, 780, 4, 320, 3, 1, 78), (2, 500, 96, 40, 5, 2, 0),
 ]
 
 
-@pytest.mark.parametrize("ver", [1, 2, 4])
+@pytest.mark.parametrize("ver", [1, 2, 4, 5])
 def test_tcgen05_generations_match_fma(ver):
     """agpt_bench_tapconv(check=1) runs the layer with the selected tcgen05 kernel and with the fp32-FMA
     kernel on the same random data and returns max |difference| (outputs are O(1))."""
