@@ -58,7 +58,7 @@ void bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, i
   out[1] = 2.0 * G * (double)L * Cin * Cout * taps / (out[0] * 1e-3) / 1e12;
   out[2] = -1.0;
   const int tcv = tc_get_version();
-  const bool raw_dbg = (tcv == 3 && taps >= 5) || tcv == 4;
+  const bool raw_dbg = (tcv == 3 && taps >= 5) || tcv == 4 || tcv == 6 || tcv == 7;
   if (dbg_avg && use_tc) {
     std::vector<long long> h((size_t)nctas * 8);
     AGPT_CUDA(cudaMemcpy(h.data(), dbgbuf.p, h.size() * 8, cudaMemcpyDeviceToHost));

@@ -34,20 +34,59 @@ __device__ __forceinline__ void epi_load(const TapConvParams& P, int g, int p, i
   }
 }
 
-__device__ __forceinline__ void epi_store(const TapConvParams& P, int g, int p, int co, float4 v, const EpiPre& pre) {
-  if (co >= P.Cout) return;
-  if (P.bias) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + co));
-    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+// split form for register-tight callers: the additive term early, the old accumulator at use
+__device__ __forceinline__ float4 epi_load_a(const TapConvParams& P, int g, int p, int co) {
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (co >= P.Cout) return a;
+  switch (P.epi) {
+    case EPI_RES:
+    case EPI_ACC:
+    case EPI_GATE:
+    case EPI_GEGLU:
+      if (P.res) a = __ldg(reinterpret_cast<const float4*>(P.res + g * P.res_gstride + (long)p * P.res_pitch + co));
+      break;
+    case EPI_DIFFOUT:
+      if (co < P.csplit) a = *reinterpret_cast<const float4*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + co);
+      else if (P.accumulate)
+        a = *reinterpret_cast<const float4*>(P.out2 + g * P.out2_gstride + (long)p * P.out2_pitch + (co - P.csplit));
+      break;
+    default: break;
   }
+  return a;
+}
+__device__ __forceinline__ float4 epi_load_b(const TapConvParams& P, int g, int p, int co) {
+  if (co < P.Cout && P.epi == EPI_ACC && P.accumulate)
+    return *reinterpret_cast<const float4*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + co);
+  return make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// per-(sample, output-channel) additive vector: bias (+ the EPI_ADDVEC vector).  Depends on (g, co) only, so
+// a caller whose items share the channel group loads it once per block instead of once per item.
+__device__ __forceinline__ float4 epi_colvec(const TapConvParams& P, int g, int co) {
+  float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (co >= P.Cout) return c;
+  if (P.bias) c = __ldg(reinterpret_cast<const float4*>(P.bias + co));
+  if (P.epi == EPI_ADDVEC) {
+    const float4 e = __ldg(reinterpret_cast<const float4*>(P.evec + (long)g * P.evec_gstride + co));
+    c.x += e.x; c.y += e.y; c.z += e.z; c.w += e.w;
+  }
+  return c;
+}
+
+__device__ __forceinline__ void epi_store_cv(const TapConvParams& P, int g, int p, int co, float4 v, const EpiPre& pre,
+                                             const float4 cv) {
+  if (co >= P.Cout) return;
+  v.x += cv.x; v.y += cv.y; v.z += cv.z; v.w += cv.w;
   switch (P.epi) {
     case EPI_BIAS: break;
     case EPI_RES:
     case EPI_ACC: {
       v.x += pre.a.x; v.y += pre.a.y; v.z += pre.a.z; v.w += pre.a.w;
       if (P.epi == EPI_ACC) {
-        v.x *= P.scale; v.y *= P.scale; v.z *= P.scale; v.w *= P.scale;
-        v.x += pre.b.x; v.y += pre.b.y; v.z += pre.b.z; v.w += pre.b.w;
+        // explicit mul then add (no FMA contraction): bit-identical to the TMA epilogue, which stages
+        // scale * (...) and lets the reduce-add store do the accumulation
+        v.x = __fadd_rn(__fmul_rn(v.x, P.scale), pre.b.x); v.y = __fadd_rn(__fmul_rn(v.y, P.scale), pre.b.y);
+        v.z = __fadd_rn(__fmul_rn(v.z, P.scale), pre.b.z); v.w = __fadd_rn(__fmul_rn(v.w, P.scale), pre.b.w);
       }
       break;
     }
@@ -63,11 +102,7 @@ __device__ __forceinline__ void epi_store(const TapConvParams& P, int g, int p, 
     case EPI_SILU:
       v.x = siluf_(v.x); v.y = siluf_(v.y); v.z = siluf_(v.z); v.w = siluf_(v.w);
       break;
-    case EPI_ADDVEC: {
-      const float4 e = __ldg(reinterpret_cast<const float4*>(P.evec + (long)g * P.evec_gstride + co));
-      v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
-      break;
-    }
+    case EPI_ADDVEC: break;   // the vector is part of cv
     case EPI_GATE:
     case EPI_GEGLU: {
       v.x += pre.a.x; v.y += pre.a.y; v.z += pre.a.z; v.w += pre.a.w;   // pre-activation term (DiffNet conditioner)
@@ -104,6 +139,10 @@ __device__ __forceinline__ void epi_store(const TapConvParams& P, int g, int p, 
     default: break;
   }
   *reinterpret_cast<float4*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + co) = v;
+}
+
+__device__ __forceinline__ void epi_store(const TapConvParams& P, int g, int p, int co, float4 v, const EpiPre& pre) {
+  epi_store_cv(P, g, p, co, v, pre, epi_colvec(P, g, co));
 }
 
 __device__ __forceinline__ void tc_epilogue(const TapConvParams& P, int g, int p, int co, float4 v) {

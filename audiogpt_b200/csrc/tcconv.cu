@@ -317,7 +317,8 @@ int tc_get_version() {
   int& ver = g_tc_version;
   if (ver < 0) {
     const char* e = getenv("AGPT_TC_V");
-    ver = e ? atoi(e) : 5;   // default: v5 (fp16 hi/lo operands); 2 = the tf32 hi/lo kernel; 3/4 = persistent tf32 (experimental)
+    ver = e ? atoi(e) : 6;   // default: v6 (persistent fp16 hi/lo, TMA epilogue) with v5 for single-wave grids; 5 = v5 only;
+                             // 2 = the tf32 hi/lo kernel; 3/4 = persistent tf32 (experimental); 7 = v6 forced
   }
   static bool env_done = false;
   if (!env_done) {
@@ -338,7 +339,8 @@ void tcconv_launch(TapConvParams P, cudaStream_t st) {
   // measured +10..60 % on the k=7/11 HiFi-GAN convs); for k <= 3 and 1-tap GEMM-like layers the
   // concurrent transform/epilogue starve on shared-memory bandwidth and v2 is faster
   // (profiles/r1b_conv_microbench.txt).  AGPT_TC_V=3x forces v3 everywhere, =2 disables it.
-  if (ver == 5 && tcconv5_launch(P, st)) return;
+  if ((ver == 6 || ver == 7) && tcconv6_launch(P, st, ver == 7)) return;   // persistent fp16 (7: also for single-wave grids)
+  if (ver >= 5 && tcconv5_launch(P, st)) return;
   if ((ver == 3 && P.ntaps >= 5) || ver == 4) {
     if (tcconv3_launch(P, st)) return;
   }   // persistent, overlapped epilogue

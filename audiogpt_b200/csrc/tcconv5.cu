@@ -17,17 +17,16 @@
 // Everything else is v2: K-major SWIZZLE_128B tiles, a conv tap = a row-shifted descriptor start
 // address, 8 worker warps (transform, then epilogue), warp 4 = MMA issuer, warp 5 = weight producer
 // (cp.async.bulk), mbarrier full/empty rings.
-#include <cuda_fp16.h>
 #include "tapconv.cuh"
 #include "tapconv_epi.cuh"
 #include "tc_common.cuh"
+#include "tc_h16.cuh"
 #include "models.h"
 
 namespace agpt {
 
 namespace {
 
-constexpr int H_KCH = 64;                   // channels per K chunk = one 128-byte swizzle span of fp16
 constexpr int MAX_NA = 4, MAX_NW = 8;
 constexpr int kMaxDyn = 227 * 1024 - 256;   // the kernel also has a small static __shared__ block
 
@@ -46,41 +45,6 @@ __host__ __device__ inline void tc5_layout(Tc5Smem& s, int BN, int RRA, int NA, 
   s.bars = o; o += 32 * 8;
   s.tmem_slot = o; o += 16;
   s.total = o;
-}
-
-__device__ __forceinline__ float4 pro_apply5(const TapConvParams& P, float4 v, bool ok, const float* pv) {
-  if (P.pro == PRO_LRELU) {
-    v.x = lrelu(v.x, P.slope); v.y = lrelu(v.y, P.slope); v.z = lrelu(v.z, P.slope); v.w = lrelu(v.w, P.slope);
-  } else if (P.pro == PRO_ADDVEC) {
-    if (ok) {
-      const float4 a = *reinterpret_cast<const float4*>(pv);
-      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-    }
-  } else if (P.pro == PRO_SILU) {
-    v.x = siluf_(v.x); v.y = siluf_(v.y); v.z = siluf_(v.z); v.w = siluf_(v.w);
-  }
-  return v;
-}
-
-// two floats -> packed f16x2 (round to nearest, saturate to +-65504): lower half = a, upper half = b
-__device__ __forceinline__ uint32_t f2h2_sat(float a, float b) {
-  uint32_t r;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-  return r;
-}
-// hi/lo split of two floats; returns the packed hi pair, writes the packed lo pair
-__device__ __forceinline__ uint32_t split2(float a, float b, uint32_t& lo) {
-  const uint32_t h = f2h2_sat(a, b);
-  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h));
-  lo = f2h2_sat(a - hf.x, b - hf.y);
-  return h;
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 constexpr int V5_THREADS = 320;   // 8 worker warps (0-3, 6-9) + warp 4 (MMA issuer) + warp 5 (weight producer)
@@ -291,12 +255,14 @@ __global__ void __launch_bounds__(NWK == 256 ? V5_THREADS : 192, 1) tcconv5_kern
                           __uint_as_float(rg[4 * qd + 2]) * dsc, __uint_as_float(rg[4 * qd + 3]) * dsc);
       }
       named_bar_sync(1, NWK);
+      const int jc = xt & 7;                       // all items of this thread share the 4-channel group
+      const float4 cv = epi_colvec(P, g, co0 + cb + 4 * jc);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int idx = xt + i * NWK;
-        const int row = (idx >> 3) & (TC_ROWS - 1), j = idx & 7;   // pp[i] < 0 for i >= nitem
+        const int row = (idx >> 3) & (TC_ROWS - 1);   // pp[i] < 0 for i >= nitem
         if (pp[i] >= 0)
-          epi_store(P, g, pp[i], co0 + cb + 4 * j, *reinterpret_cast<const float4*>(stg + sw128(row, j)), pre[i]);
+          epi_store_cv(P, g, pp[i], co0 + cb + 4 * jc, *reinterpret_cast<const float4*>(stg + sw128(row, jc)), pre[i], cv);
       }
       if (cb + 32 < BN) load_block(cb + 32);
       // staging halves alternate; a half is rewritten two blocks later, after the next named
@@ -305,7 +271,9 @@ __global__ void __launch_bounds__(NWK == 256 ? V5_THREADS : 192, 1) tcconv5_kern
     if (dbg_on && tid == 0) dbg[5] = clock64();
   } else if (warp == 4) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // the whole warp runs the loop (converged waits); one ELECTED lane issues, so that ptxas keeps the
+    // descriptors in uniform registers instead of a per-MMA divergence "waterfall"
+    {
       // kind::f16: D = F32 (bit 4), A = B = F16 (format 0), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
       const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
       long long dbg_wa = 0, dbg_ww = 0;
@@ -317,7 +285,7 @@ __global__ void __launch_bounds__(NWK == 256 ? V5_THREADS : 192, 1) tcconv5_kern
         long long tw0 = dbg_on ? clock64() : 0;
         mbar_wait(&a_full[buf], (uint32_t)((c / NA) & 1));
         tc_fence_after();
-        if (dbg_on) { const long long t1 = clock64(); if (c == 0) dbg[2] = t1; dbg_wa += t1 - tw0; }
+        if (dbg_on) { const long long t1 = clock64(); if (c == 0 && lane == 0) dbg[2] = t1; dbg_wa += t1 - tw0; }
         const uint32_t ahi0 = smem_u32(smem + S.a_hi[buf]), alo0 = smem_u32(smem + S.a_lo[buf]);
         for (int t = 0; t < ntaps; ++t, ++it) {
           const int s = it % NW;
@@ -329,18 +297,23 @@ __global__ void __launch_bounds__(NWK == 256 ? V5_THREADS : 192, 1) tcconv5_kern
           const uint64_t dah = make_desc(ahi0 + shift), dal = make_desc(alo0 + shift);
           const uint64_t dwh = make_desc(smem_u32(smem + S.w[s]));
           const uint64_t dwl = make_desc(smem_u32(smem + S.w[s] + BN * 128));
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ko = (uint64_t)((k * 32) >> 4);
-            umma_f16(tmem_base, dah + ko, dwh + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
-            umma_f16(tmem_base, dal + ko, dwh + ko, idesc, 1u);
-            umma_f16(tmem_base, dah + ko, dwl + ko, idesc, 1u);
+          if (elect_one()) {
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ko = (uint64_t)((k * 32) >> 4);
+              umma_f16(tmem_base, dah + ko, dwh + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              umma_f16(tmem_base, dal + ko, dwh + ko, idesc, 1u);
+              umma_f16(tmem_base, dah + ko, dwl + ko, idesc, 1u);
+            }
+            umma_commit(&w_empty[s]);
+            if (t == ntaps - 1) {
+              umma_commit(&a_empty[buf]);
+              if (c == nchunks - 1) umma_commit(acc_full);
+            }
           }
-          umma_commit(&w_empty[s]);
+          __syncwarp();
         }
-        umma_commit(&a_empty[buf]);
       }
-      umma_commit(acc_full);
-      if (dbg_on) { dbg[3] = clock64(); dbg[6] = dbg_wa; dbg[7] = dbg_ww; }
+      if (dbg_on && lane == 0) { dbg[3] = clock64(); dbg[6] = dbg_wa; dbg[7] = dbg_ww; }
     }
   } else if (warp == 5) {
     // =========================== weight producer ===========================

@@ -268,7 +268,7 @@ def run_ours(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "tapconv_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
-    variants = ["fma_BN128", "fma_BN64", "fma_BN32", "tcgen05_3xTF32"]
+    variants = ["fma_BN128", "fma_BN64", "fma_BN32", "tcgen05_3xFP16"]
     tc_on = lnv[3] > 0
     per_variant = {variants[i]: {"launches": int(lnv[i]), "ms": msv[i],
                                  "tflops": (flv[i] / (msv[i] * 1e-3) / 1e12) if msv[i] > 0 else None,
@@ -280,19 +280,20 @@ def run_ours(args):
            "note": "algorithmic bytes (in+out+residual+weights per launch); the path is compute-bound "
                    "(AI ~ 10^3 FLOP/B, SURVEY.md 8d) so this fraction is small by construction"}
     if tc_on:
-        # tcgen05.mma.kind::tf32 with 3 error-compensated products per algorithmic MAC: the tensor pipe
-        # executes 3x the algorithmic FLOPs.  TF32 issues at half the BF16 rate, so the measured cuBLAS
-        # bf16 number (MEASURED_PEAKS.json, burst figure: kernels are timed one by one) is halved.
-        bf16 = float(peaks.get("bf16_tflops", 1590.0))
-        tf32_peak = bf16 / 2.0
+        # tcgen05.mma.kind::f16 on fp16 hi/lo operand parts, 3 error-compensated products per algorithmic
+        # MAC: the tensor pipe executes 3x the algorithmic FLOPs.  Denominator: the measured cuBLAS bf16
+        # number (MEASURED_PEAKS.json, burst figure: kernels are timed one by one); fp16 and bf16 issue at
+        # the same rate.
+        f16_peak = float(peaks.get("bf16_tflops", 1590.0))
         roofline = {
-            "kernel": "tcconv2_kernel<BN> (tcgen05 tapconv, 3xTF32; all contractions of the generator)",
-            "bound": "tensor", "achieved": 3.0 * ach_tf, "peak": tf32_peak, "unit": "TFLOP/s",
-            "frac": 3.0 * ach_tf / tf32_peak,
+            "kernel": "tcconv6_kernel<BN,NI> / tcconv5_kernel<BN,NWK> (tcgen05 tap-GEMM, 3 x fp16 hi/lo products; "
+                      "all contractions of the generator)",
+            "bound": "tensor", "achieved": 3.0 * ach_tf, "peak": f16_peak, "unit": "TFLOP/s",
+            "frac": 3.0 * ach_tf / f16_peak,
             "achieved_algorithmic_tflops": ach_tf,
-            "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst) / 2 for kind::tf32" if peaks else
-                            "fallback 1.59 PFLOP/s bf16 / 2 for kind::tf32"),
-            "note": "achieved counts the tensor-pipe FLOPs actually issued (3 TF32 products per fp32-grade MAC); "
+            "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst); kind::f16 issues at the bf16 rate" if peaks else
+                            "fallback 1.59 PFLOP/s dense bf16/fp16"),
+            "note": "achieved counts the tensor-pipe FLOPs actually issued (3 fp16 products per fp32-grade MAC); "
                     "the algorithmic rate is achieved/3",
             "fp32_fma_peak_tflops_measured": fma_peak,
             "algorithmic_vs_fp32_fma_peak": ach_tf / fma_peak if fma_peak > 0 else None,

@@ -20,14 +20,15 @@ sel = sys.argv[1:]
 for name, G, Ln, Cin, Cout, K, dil, Wr in shapes:
     if sel and not any(s in name for s in sel): continue
     res = {}
-    for ver in (5, 2):
+    VA, VB = int(os.environ.get('VA', 7)), int(os.environ.get('VB', 5))
+    for ver in (VA, VB):
         _lib.check(L.agpt_set_tc_version(ver))
         out = (C.c_double * 3)(); dbg = (C.c_double * 8)()
         _lib.check(L.agpt_bench_tapconv(G, Ln, Cin, Cout, K, dil, Wr, 1, 1, 5, 1, out, dbg))
         res[ver] = (list(out), list(dbg))
     o2 = (C.c_double * 3)()
     _lib.check(L.agpt_bench_tapconv(G, Ln, Cin, Cout, K, dil, Wr, 1, 0, 3, 0, o2, None))
-    o5, d = res[5]; ov2, dv2 = res[2]
-    print(f"{name:22s} v5 {o5[0]*1e3:8.1f} us {o5[1]:6.1f} TF d={o5[2]:.1e} | v2 {ov2[0]*1e3:8.1f} us {ov2[1]:6.1f} TF d={ov2[2]:.1e} | fma {o2[0]*1e3:8.1f} us | "
-          f"v5 cyc setup {d[0]:.0f} firstA {d[1]:.0f} mma {d[2]:.0f} drain {d[3]:.0f} epi {d[4]:.0f} total {d[5]:.0f} waitA {d[6]:.0f} waitW {d[7]:.0f} | v2 mma {dv2[2]:.0f} total {dv2[5]:.0f}", flush=True)
+    o5, d = res[VA]; ov2, dv2 = res[VB]
+    print(f"{name:22s} vA {o5[0]*1e3:8.1f} us {o5[1]:6.1f} TF d={o5[2]:.1e} | vB {ov2[0]*1e3:8.1f} us {ov2[1]:6.1f} TF d={ov2[2]:.1e} | fma {o2[0]*1e3:8.1f} us | "
+          f"vA dbg " + " ".join(f"{x:.0f}" for x in d) + " | vB dbg " + " ".join(f"{x:.0f}" for x in dv2), flush=True)
 _lib.check(L.agpt_set_tc_version(-1))

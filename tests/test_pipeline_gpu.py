@@ -80,7 +80,7 @@ SHAPES = [  # G, L, Cin, Cout, K, dil, Wreal
 ]
 
 
-@pytest.mark.parametrize("ver", [1, 2, 4, 5])
+@pytest.mark.parametrize("ver", [1, 2, 4, 5, 6, 7])
 def test_tcgen05_generations_match_fma(ver):
     """agpt_bench_tapconv(check=1) runs the layer with the selected tcgen05 kernel and with the fp32-FMA
     kernel on the same random data and returns max |difference| (outputs are O(1))."""
