@@ -40,6 +40,11 @@ int agpt_version(void) { return 100; }
 long long agpt_launch_count(void) { return g_launches.load(); }
 
 int agpt_profile_enable(int on) { return guarded([&] { profile_enable(on); }); }
+long agpt_profile_dump(char* out, long cap) {
+  long n = -1;
+  guarded([&] { n = profile_dump(out, cap); });
+  return n;
+}
 int agpt_profile_collect(double ms[4], double flops[4], double bytes[4], long long launches[4]) {
   return guarded([&] { profile_collect(ms, flops, bytes, launches); });
 }

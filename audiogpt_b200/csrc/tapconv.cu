@@ -6,7 +6,7 @@
 namespace agpt {
 
 // ---- optional per-launch CUDA-event profiling (bench.py's roofline leg) ----
-struct ProfRec { cudaEvent_t e0, e1; int variant; double flops, bytes; };
+struct ProfRec { cudaEvent_t e0, e1; int variant; double flops, bytes; int G, L, Cin, Cout, ntaps, span, epi, Wreal; };
 static bool g_prof = false;
 static std::vector<ProfRec> g_recs;
 
@@ -27,6 +27,22 @@ void profile_collect(double* ms, double* flops, double* bytes, long long* launch
     AGPT_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
     ms[r.variant] += t; flops[r.variant] += r.flops; bytes[r.variant] += r.bytes; launches[r.variant] += 1;
   }
+}
+
+// One text line per recorded launch: "variant G L Cin Cout ntaps span epi Wreal ms flops" (dev tooling).
+long profile_dump(char* out, long cap) {
+  AGPT_CUDA(cudaDeviceSynchronize());
+  long n = 0;
+  for (auto& r : g_recs) {
+    float t = 0.f;
+    AGPT_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    char line[160];
+    const int len = snprintf(line, sizeof(line), "%d %d %d %d %d %d %d %d %d %.6f %.6e\n", r.variant, r.G, r.L, r.Cin, r.Cout,
+                             r.ntaps, r.span, r.epi, r.Wreal, t, r.flops);
+    if (n + len < cap) { memcpy(out + n, line, len); n += len; }
+  }
+  if (cap > 0) out[n < cap ? n : cap - 1] = 0;
+  return n;
 }
 
 // ---- fp32 FMA saturation probe: the measured denominator of the compute roofline ----
@@ -247,6 +263,10 @@ void tapconv_launch(TapConvParams P, cudaStream_t st) {
     rec->bytes = 4.0 * (rows * P.Cin + rows * out_c + (P.res ? rows * P.Cout : 0.0) +
                         (P.epi == EPI_ACC && P.accumulate ? rows * P.Cout : 0.0) +
                         (double)P.ntaps * P.Cin * P.Cout);
+    rec->G = P.G; rec->L = P.L; rec->Cin = P.Cin; rec->Cout = P.Cout; rec->ntaps = P.ntaps; rec->epi = P.epi; rec->Wreal = P.Wreal;
+    { int lo = P.tap_off[0], hi = P.tap_off[0];
+      for (int t = 1; t < P.ntaps; ++t) { lo = std::min(lo, P.tap_off[t]); hi = std::max(hi, P.tap_off[t]); }
+      rec->span = hi - lo; }
     AGPT_CUDA(cudaEventCreate(&rec->e0));
     AGPT_CUDA(cudaEventCreate(&rec->e1));
     AGPT_CUDA(cudaEventRecord(rec->e0, st));

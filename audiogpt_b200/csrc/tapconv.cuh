@@ -56,7 +56,7 @@ struct TapConvParams {
   float* out2; long out2_gstride; int out2_pitch; int csplit;
   const float* w_tc256;   // optional BN=256 image (layers with Cout % 256 == 0)
   const float* w_h; const float* w_h256; int tc_chunks_h; float tc_descale;   // fp16 hi/lo image (tcconv5.cu): 64-channel chunks, weights pre-scaled by 1/tc_descale
-  const float* w_tc; int tc_bn, tc_chunks, tc_na, tc_nw, tc_nr, tc_nwk, tc_nb, tc_flags, tc_flags_user;
+  const float* w_tc; int tc_bn, tc_chunks, tc_na, tc_nw, tc_nr, tc_nwk, tc_nb, tc_tps, tc_flags, tc_flags_user;
   long long* dbg;      // optional per-CTA phase timestamps (tc_flags & 2)   // tensor-core weight image (tcconv.cu); tc_bn == 0 => FMA only
   float flops_scale;   // useful fraction of the MACs (zero-padded polyphase taps); 0 => 1
 };
@@ -97,6 +97,7 @@ int tc_get_version();
 bool tc_enabled();
 void profile_enable(int on);
 void profile_collect(double* ms, double* flops, double* bytes, long long* launches);
+long profile_dump(char* out, long cap);
 double fma_peak_tflops();
 
 // Common setup from a PackedConv; caller fills in/out/pro/epi afterwards.

@@ -62,6 +62,16 @@ __device__ __forceinline__ bool elect_one() {
       : "+r"(laneid), "+r"(pred) : "r"(0xFFFFFFFFu));
   return pred != 0;
 }
+// explicit 128-bit shared-memory accesses (address = shared-window offset): volatile, so they are issued in
+// program order -- used where several loads must be in flight before the first dependent store
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 // streaming 128-bit global load that does not allocate in L1 (activations are read once per CTA)
 __device__ __forceinline__ float4 ldg_stream(const float* p) {
   float4 v;

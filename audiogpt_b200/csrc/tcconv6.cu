@@ -37,15 +37,16 @@ struct Tc6Smem {
   uint32_t a_hi[MAX_NA6], a_lo[MAX_NA6], w[MAX_NW6], stg, cvs, rowinfo, rowp, bars, tmem_slot, total;
 };
 constexpr int V6_EBLK = TC_ROWS * 128;   // one epilogue block buffer: 128 rows x 32 fp32 columns (4 KB per epilogue warp)
+constexpr uint32_t V6_FLAG_WBLK = 2048;  // tc_flags bit: TMA epilogue with whole-block [128 x 32] boxes
 constexpr uint32_t V6_FLAG_TMA = 64;     // tc_flags bit: epilogue through tensor maps (TMA load / store / reduce-add)
-__host__ __device__ inline void tc6_layout(Tc6Smem& s, int BN, int RRA, int NA, int NW, int NB) {
+__host__ __device__ inline void tc6_layout(Tc6Smem& s, int BN, int RRA, int NA, int NW, int NB, int tps) {
   uint32_t o = 0;
   for (int i = 0; i < MAX_NA6; ++i) { s.a_hi[i] = o; if (i < NA) o += RRA * 128; }
   for (int i = 0; i < MAX_NA6; ++i) { s.a_lo[i] = o; if (i < NA) o += RRA * 128; }
-  for (int i = 0; i < MAX_NW6; ++i) { s.w[i] = o; if (i < NW) o += 2 * BN * 128; }
+  for (int i = 0; i < MAX_NW6; ++i) { s.w[i] = o; if (i < NW) o += tps * 2 * BN * 128; }
   s.stg = o; o += (NB > 1 ? NB : 1) * V6_EBLK;   // epilogue block buffers (warp-private 32-row slices), 1 KB aligned
   s.cvs = o; o += 4 * 256 * 4;         // per-epilogue-warp copy of the tile's bias (+ per-sample vector)
-  s.rowinfo = o; o += 2 * RRA * 4;     // ring of 2 tiles
+  s.rowinfo = o; o += 4 * RRA * 4;     // ring of 4 tiles
   s.rowp = o; o += 2 * TC_ROWS * 4;    // ring of 2 tiles
   o = (o + 15) & ~15u;
   s.bars = o; o += 48 * 8;
@@ -64,7 +65,7 @@ __device__ __forceinline__ TileId6 tile_of6(int t, int nct, int nrt) {
 }
 
 // NI = register-prefetched 8-channel items per transform thread (rows r0, r0+32, ...): covers RRA <= 32 * NI
-template <int BN, int NI>
+template <int BN, int NI, bool NARROW>
 __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_constant__ TapConvParams P,
                                                                 const __grid_constant__ CUtensorMap tm_res,
                                                                 const __grid_constant__ CUtensorMap tm_out) {
@@ -72,7 +73,8 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
   const int RRA = P.R, NA = P.tc_na, NW = P.tc_nw;
   __shared__ Tc6Smem S;
-  if (threadIdx.x == 0) tc6_layout(S, BN, RRA, NA, NW, P.tc_nb);
+  const int tps = P.tc_tps;                  // taps per weight stage
+  if (threadIdx.x == 0) tc6_layout(S, BN, RRA, NA, NW, P.tc_nb, tps);
   __syncthreads();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S.bars);
   uint64_t* a_full = bars + 0;             // [MAX_NA6]
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
   const int nct = (P.Cout + BN - 1) / BN, nrt = (Lv + TC_ROWS - 1) / TC_ROWS;
   const int ntiles = nct * nrt * P.G;
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  constexpr uint32_t TMEM_COLS = (BN <= 64) ? 512 : 2 * BN;   // (BN <= 64: room for the split-chain experiment, flag 512)
 
   if (tid == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], V6_NT); mbar_init(&a_empty[i], 1); }
@@ -120,21 +122,26 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
 
   if (warp >= 6) {
     // =========================== transform warps ===========================
+    // Thread mapping: QN 16-byte fp16 chunks (8 channels each) per row, 256 / QN rows per pass.  NARROW
+    // (Cin <= 32: only 4 chunks per row are ever touched) uses all threads on 64 rows per pass and keeps
+    // TWO register sets in flight (chunks k+1 and k+2), because with one tile = one chunk the single-depth
+    // prefetch leaves the global-load latency exposed once per tile.
+    constexpr int QN = NARROW ? 4 : 8, RSTR = V6_NT / QN;
     const int xt = tid - 6 * 32;                   // 0..255
     int* rowinfo_ring = reinterpret_cast<int*>(smem + S.rowinfo);
-    float4 v0[NI], v1[NI];
-    uint32_t ok0 = 0, ok1 = 0;
-    const int q = xt & 7, r0 = xt >> 3;            // this thread: 16-byte fp16 chunk q (8 channels) of rows r0, r0+32, ...
+    struct RSet { float4 v0[NI], v1[NI]; uint32_t ok0, ok1; };
+    RSet RA, RB;
+    const int q = xt % QN, r0 = xt / QN;
     const int total_gc = my_tiles * nchunks;
 
-    // prefetch global chunk k (tile k / nchunks, chunk k % nchunks) into registers
-    auto prefetch = [&](int k) {
+    // prefetch global chunk k (tile k / nchunks, chunk k % nchunks) into a register set
+    auto prefetch = [&](int k, RSet& R) {
       const int tl = k / nchunks, c = k - tl * nchunks;
       const TileId6 T = tile_of6((int)blockIdx.x + tl * (int)gridDim.x, nct, nrt);
-      int* rowinfo = rowinfo_ring + (tl & 1) * RRA;
+      int* rowinfo = rowinfo_ring + (tl & 3) * RRA;
       if (c == 0) {
-        // the previous tile's table is no longer read by anyone: every thread passes this barrier only
-        // after its prefetches of tile tl-1 were issued, and tile tl-2's slot is the one rewritten
+        // ring of 4 tiles: a slot is rewritten three tiles later; every thread passes this barrier only
+        // after its own reads of the older tables were issued
         for (int i = xt; i < RRA; i += V6_NT) {
           const int qq = T.q0 + lo + i;
           int a = -1;
@@ -154,23 +161,21 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
       const uint32_t ri_sh = smem_u32(rowinfo);
       const int ch = c * H_KCH + 8 * q;
       const bool chok0 = ch < P.Cin, chok1 = ch + 4 < P.Cin;
-      ok0 = 0; ok1 = 0;
+      R.ok0 = 0; R.ok1 = 0;
 #pragma unroll
       for (int u = 0; u < NI; ++u) {
-        const int row = r0 + 32 * u;
+        const int row = r0 + RSTR * u;
         int a = -1;
         if (row < RRA) asm volatile("ld.shared.s32 %0, [%1];" : "=r"(a) : "r"(ri_sh + 4u * (uint32_t)row));
         const bool k0 = chok0 && (a >= 0), k1 = chok1 && (a >= 0);
-        if (P.tc_flags & 16) { v0[u] = make_float4(1.f, 2.f, 3.f, 4.f); v1[u] = v0[u]; continue; }   // experiment: no global reads
-        v0[u] = ldg_stream(k0 ? (ing + a + ch) : P.in);      // zero-select happens at use
-        v1[u] = ldg_stream(k1 ? (ing + a + ch + 4) : P.in);
-        ok0 |= (k0 ? 1u : 0u) << u;
-        ok1 |= (k1 ? 1u : 0u) << u;
+        R.v0[u] = ldg_stream(k0 ? (ing + a + ch) : P.in);      // zero-select happens at use
+        R.v1[u] = ldg_stream(k1 ? (ing + a + ch + 4) : P.in);
+        R.ok0 |= (k0 ? 1u : 0u) << u;
+        R.ok1 |= (k1 ? 1u : 0u) << u;
       }
     };
-
-    if (total_gc > 0) prefetch(0);
-    for (int k = 0; k < total_gc; ++k) {
+    // prologue + fp16 hi/lo split of register set R -> operand buffer of global chunk k
+    auto convert = [&](int k, const RSet& R) {
       const int buf = k % NA, n = k / NA;
       const int tl = k / nchunks, c = k - tl * nchunks;
       const int kv = min(H_KCH, P.Cin - c * H_KCH);
@@ -186,12 +191,12 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
       if (q < nq) {
 #pragma unroll
         for (int u = 0; u < NI; ++u) {
-          const int row = r0 + 32 * u;
+          const int row = r0 + RSTR * u;
           if (row < RRA) {
-            const bool k0 = (ok0 >> u) & 1u, k1 = (ok1 >> u) & 1u;
+            const bool k0 = (R.ok0 >> u) & 1u, k1 = (R.ok1 >> u) & 1u;
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 x0 = pro_apply5(P, k0 ? v0[u] : z, k0, pvg);
-            const float4 x1 = pro_apply5(P, k1 ? v1[u] : z, k1, pvg ? pvg + 4 : nullptr);
+            const float4 x0 = pro_apply5(P, k0 ? R.v0[u] : z, k0, pvg);
+            const float4 x1 = pro_apply5(P, k1 ? R.v1[u] : z, k1, pvg ? pvg + 4 : nullptr);
             uint4 h, l;
             h.x = split2(x0.x, x0.y, l.x);
             h.y = split2(x0.z, x0.w, l.y);
@@ -205,50 +210,83 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
       }
       fence_proxy_async();
       mbar_arrive(&a_full[buf]);
-      if (k + 1 < total_gc) prefetch(k + 1);     // in flight while this thread waits for the next a_empty
+    };
+
+    if (NARROW) {
+      if (total_gc > 0) prefetch(0, RA);
+      if (total_gc > 1) prefetch(1, RB);
+      for (int k = 0; k < total_gc; k += 2) {
+        convert(k, RA);
+        if (k + 2 < total_gc) prefetch(k + 2, RA);
+        if (k + 1 < total_gc) {
+          convert(k + 1, RB);
+          if (k + 3 < total_gc) prefetch(k + 3, RB);
+        }
+      }
+    } else {
+      if (total_gc > 0) prefetch(0, RA);
+      for (int k = 0; k < total_gc; ++k) {
+        convert(k, RA);
+        if (k + 1 < total_gc) prefetch(k + 1, RA);     // in flight while this thread waits for the next a_empty
+      }
     }
   } else if (warp == 4) {
     // =========================== MMA issuer ===========================
-    // the whole warp runs the loop (converged waits); one ELECTED lane issues, so that ptxas keeps the
-    // descriptors in uniform registers instead of a per-MMA divergence "waterfall"
+    // The whole warp runs the loop (converged waits); one ELECTED lane issues, so that ptxas keeps the
+    // descriptors in uniform registers instead of a per-MMA divergence "waterfall".  A weight stage holds
+    // `tps` taps (~32 KB), so the per-stage handshake (wait, commit, scalar bookkeeping -- a few hundred
+    // cycles of dependent single-warp code) is paid once per 12-48 MMAs even on the narrow layers.
     {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+      const uint64_t DC = make_desc(0);                         // descriptor constants; the low 14 bits take (address >> 4)
+      const uint32_t a16 = smem_u32(smem + S.a_hi[0]) >> 4;     // operand ring: hi tiles, then lo tiles
+      const uint32_t abuf16 = (uint32_t)(RRA * 128) >> 4;       // one hi (or lo) tile
+      const uint32_t alo16 = (uint32_t)NA * abuf16;             // hi -> lo distance
+      const uint32_t w16 = smem_u32(smem + S.w[0]) >> 4;
+      const uint32_t wtap16 = (uint32_t)(2 * BN * 128) >> 4;    // one tap (hi | lo) inside a stage
+      const uint32_t wstage16 = (uint32_t)tps * wtap16;
+      constexpr uint32_t wlo16 = (uint32_t)(BN * 128) >> 4;
       int gc = 0, it = 0;
       for (int tl = 0; tl < my_tiles; ++tl) {
         const int acc = tl & 1, na = tl >> 1;
         if (na >= 1) { DBG_WAIT6(3, mbar_wait(&acc_empty[acc], (uint32_t)((na - 1) & 1))); tc_fence_after(); }
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        bool first = true;
+        uint32_t nz = 0;                                        // 0 for the very first MMA of the tile
         for (int c = 0; c < nchunks; ++c, ++gc) {
           const int buf = gc % NA;
           const int kv = min(H_KCH, P.Cin - c * H_KCH);
           const int ksteps = (kv + 15) >> 4;
           DBG_WAIT6(1, mbar_wait(&a_full[buf], (uint32_t)((gc / NA) & 1)));
           tc_fence_after();
-          const uint32_t ahi0 = smem_u32(smem + S.a_hi[buf]), alo0 = smem_u32(smem + S.a_lo[buf]);
-          for (int t = 0; t < ntaps; ++t, ++it) {
+          const uint64_t dA = DC + (uint64_t)(a16 + (uint32_t)buf * abuf16);
+          for (int t0 = 0; t0 < ntaps; t0 += tps, ++it) {
             const int s = it % NW;
+            const int t1 = min(ntaps, t0 + tps);
             DBG_WAIT6(2, mbar_wait(&w_full[s], (uint32_t)((it / NW) & 1)));
             tc_fence_after();
-            const uint32_t shift = (uint32_t)(P.tap_off[t] - lo) * 128u;
-            const uint64_t dah = make_desc(ahi0 + shift), dal = make_desc(alo0 + shift);
-            const uint64_t dwh = make_desc(smem_u32(smem + S.w[s]));
-            const uint64_t dwl = make_desc(smem_u32(smem + S.w[s] + BN * 128));
+            const uint64_t dW = DC + (uint64_t)(w16 + (uint32_t)s * wstage16);
             if (elect_one()) {
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t ko = (uint64_t)((k * 32) >> 4);
-                umma_f16(tmem_d, dah + ko, dwh + ko, idesc, (first && k == 0) ? 0u : 1u);
-                umma_f16(tmem_d, dal + ko, dwh + ko, idesc, 1u);
-                umma_f16(tmem_d, dah + ko, dwl + ko, idesc, 1u);
+              for (int t = t0; t < t1; ++t) {
+                const uint64_t dah = dA + (uint64_t)((uint32_t)(P.tap_off[t] - lo) * 8u);   // one row = 128 B = 8 x 16 B
+                const uint64_t dal = dah + alo16;
+                const uint64_t dwh = dW + (uint64_t)((uint32_t)(t - t0) * wtap16);
+                const uint64_t dwl = dwh + wlo16;
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint64_t ko = (uint64_t)(2 * k);        // 32 bytes per k-step
+                  umma_f16(tmem_d, dah + ko, dwh + ko, idesc, nz);
+                  nz = 1u;
+                  umma_f16(tmem_d, dal + ko, dwh + ko, idesc, 1u);
+                  umma_f16(tmem_d, dah + ko, dwl + ko, idesc, 1u);
+                }
               }
               umma_commit(&w_empty[s]);
-              if (t == ntaps - 1) {
+              if (t1 == ntaps) {
                 umma_commit(&a_empty[buf]);
                 if (c == nchunks - 1) umma_commit(&acc_full[acc]);
               }
             }
             __syncwarp();
-            first = false;
+            nz = 1u;
           }
         }
       }
@@ -256,16 +294,19 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
   } else if (warp == 5) {
     // =========================== weight producer ===========================
     if (lane == 0) {
-      const uint32_t bytes = 2u * BN * 128u;
+      const uint32_t tapbytes = 2u * BN * 128u;
       int it = 0;
       for (int tl = 0; tl < my_tiles; ++tl) {
         const TileId6 T = tile_of6((int)blockIdx.x + tl * (int)gridDim.x, nct, nrt);
-        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(P.w_h) + (size_t)T.ct * (size_t)iters_per_tile * bytes;
-        for (int i = 0; i < iters_per_tile; ++i, ++it) {
-          const int s = it % NW, n = it / NW;
-          if (n >= 1) DBG_WAIT6(7, mbar_wait(&w_empty[s], (uint32_t)((n - 1) & 1)));
-          mbar_arrive_expect_tx(&w_full[s], bytes);
-          bulk_g2s(smem + S.w[s], wsrc + (size_t)i * bytes, bytes, &w_full[s]);
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(P.w_h) + (size_t)T.ct * (size_t)iters_per_tile * tapbytes;
+        for (int c = 0; c < nchunks; ++c) {
+          for (int t0 = 0; t0 < ntaps; t0 += tps, ++it) {
+            const int s = it % NW, n = it / NW;
+            const uint32_t bytes = (uint32_t)(min(ntaps, t0 + tps) - t0) * tapbytes;
+            if (n >= 1) DBG_WAIT6(7, mbar_wait(&w_empty[s], (uint32_t)((n - 1) & 1)));
+            mbar_arrive_expect_tx(&w_full[s], bytes);
+            bulk_g2s(smem + S.w[s], wsrc + (size_t)(c * ntaps + t0) * tapbytes, bytes, &w_full[s]);
+          }
         }
       }
     }
@@ -281,8 +322,12 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
     const int LA = slack2 ? NB - 3 : NB - 2;
     const bool has_res = (P.epi == EPI_RES || P.epi == EPI_ACC) && P.res != nullptr;
     const bool red_add = (P.epi == EPI_ACC) && P.accumulate;
-    uint8_t* ebuf = smem + S.stg + quad * 4096;
-    uint64_t* efull = e_full + quad * 4;
+    // whole-block mode (default): ONE tensor-map op moves a [128 rows x 32 columns] block for all four warps
+    // (4x fewer TMA ops; the warps meet at a named barrier before the store).  Per-warp mode: [32 x 32] boxes.
+    const bool wb = (P.tc_flags & V6_FLAG_WBLK) != 0;
+    const bool leader = wb ? (tid == 0) : (lane == 0);
+    uint8_t* ebuf = smem + S.stg + quad * 4096;             // this warp's 32 rows inside block buffer 0
+    uint64_t* efull = wb ? e_full : e_full + quad * 4;
     float* cvs = reinterpret_cast<float*>(smem + S.cvs) + quad * 256;
     const float dsc = P.tc_descale;
     constexpr int nblk = BN / 32;
@@ -291,10 +336,15 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
       const int tl = m / nblk, b = m - tl * nblk;
       const TileId6 T = tile_of6((int)blockIdx.x + tl * (int)gridDim.x, nct, nrt);
       const int bi = m % NB;
-      mbar_arrive_expect_tx(&efull[bi], 4096u);
-      tma_load_3d(ebuf + bi * V6_EBLK, &tm_res, T.ct * BN + 32 * b, T.q0 + quad * 32, T.g, &efull[bi]);
+      if (wb) {
+        mbar_arrive_expect_tx(&efull[bi], 16384u);
+        tma_load_3d(smem + S.stg + bi * V6_EBLK, &tm_res, T.ct * BN + 32 * b, T.q0, T.g, &efull[bi]);
+      } else {
+        mbar_arrive_expect_tx(&efull[bi], 4096u);
+        tma_load_3d(ebuf + bi * V6_EBLK, &tm_res, T.ct * BN + 32 * b, T.q0 + quad * 32, T.g, &efull[bi]);
+      }
     };
-    if (lane == 0) {
+    if (leader) {
       tma_prefetch_desc(&tm_out);
       if (has_res) {
         tma_prefetch_desc(&tm_res);
@@ -322,23 +372,27 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
 #pragma unroll 1
       for (int cb = 0; cb < BN; cb += 32, ++j) {
         const int bi = j % NB;
-        if (lane == 0) {
+        const bool seg = dbg_on && (P.tc_flags & 4);
+        long long ts0 = seg ? clock64() : 0;
+        if (leader) {
           if (has_res) {
             if (slack2) tma_wait_group_read<2>();  // store j-3 (resp. j-2) has left its buffer == the buffer of block j+LA
             else tma_wait_group_read<1>();
             if (j + LA < total_blk) issue_load(j + LA);
-          } else {                                // buffer bi was last used by store j-NB
+          } else if (!wb) {                       // buffer bi was last used by store j-NB
             if (NB >= 4) tma_wait_group_read<3>();
             else if (NB == 3) tma_wait_group_read<2>();
             else tma_wait_group_read<1>();
           }
         }
-        __syncwarp();
+        if (!wb) __syncwarp();
+        if (seg) { const long long t = clock64(); dbgacc[1] += t - ts0; ts0 = t; }
         if (!acc_ready) {
           DBG_WAIT6(5, mbar_wait(&acc_full[acc], (uint32_t)((tl >> 1) & 1)));
           tc_fence_after();
           acc_ready = true;
           t_epi0 = dbg_on ? clock64() : 0;
+          if (seg) ts0 = clock64();
         }
         uint32_t rg[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + cb);
@@ -356,39 +410,68 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
           tc_fence_before();
           mbar_arrive(&acc_empty[acc]);
         }
+        if (seg) { const long long t = clock64(); dbgacc[2] += t - ts0; ts0 = t; }
         if (has_res) DBG_WAIT6(4, mbar_wait(&efull[bi], (uint32_t)((j / NB) & 1)));
         uint8_t* buf = ebuf + bi * V6_EBLK;
+        // two halves of four 16-byte cells: all shared-memory loads of a half are issued before any store
+        // (the compiler cannot prove that the in-place stores do not alias the loads and would serialise them)
+        const uint32_t buf_sh = smem_u32(buf), cvs_sh = smem_u32(cvs + cb);
 #pragma unroll
-        for (int qd = 0; qd < 8; ++qd) {
-          float4* cell = reinterpret_cast<float4*>(buf + sw128(lane, qd));
-          const float4 c4 = *reinterpret_cast<const float4*>(cvs + cb + 4 * qd);
-          float4 v = make_float4(fmaf(__uint_as_float(rg[4 * qd]), dsc, c4.x), fmaf(__uint_as_float(rg[4 * qd + 1]), dsc, c4.y),
-                                 fmaf(__uint_as_float(rg[4 * qd + 2]), dsc, c4.z), fmaf(__uint_as_float(rg[4 * qd + 3]), dsc, c4.w));
-          if (has_res) {
-            const float4 r = *cell;
-            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        for (int hh = 0; hh < 2; ++hh) {
+          float4 rr[4], cc[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int qd = 4 * hh + i;
+            if (has_res) rr[i] = lds128(buf_sh + sw128(lane, qd));
+            else rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            cc[i] = lds128(cvs_sh + 16u * (uint32_t)qd);
           }
-          switch (P.epi) {
-            case EPI_ACC: v.x = __fmul_rn(v.x, P.scale); v.y = __fmul_rn(v.y, P.scale); v.z = __fmul_rn(v.z, P.scale); v.w = __fmul_rn(v.w, P.scale); break;
-            case EPI_RELU: v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); break;
-            case EPI_TANH: v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); break;
-            case EPI_MISH: v.x = mishf_(v.x); v.y = mishf_(v.y); v.z = mishf_(v.z); v.w = mishf_(v.w); break;
-            case EPI_SILU: v.x = siluf_(v.x); v.y = siluf_(v.y); v.z = siluf_(v.z); v.w = siluf_(v.w); break;
-            default: break;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int qd = 4 * hh + i;
+            float4 v = make_float4(fmaf(__uint_as_float(rg[4 * qd]), dsc, cc[i].x), fmaf(__uint_as_float(rg[4 * qd + 1]), dsc, cc[i].y),
+                                   fmaf(__uint_as_float(rg[4 * qd + 2]), dsc, cc[i].z), fmaf(__uint_as_float(rg[4 * qd + 3]), dsc, cc[i].w));
+            v.x += rr[i].x; v.y += rr[i].y; v.z += rr[i].z; v.w += rr[i].w;
+            switch (P.epi) {
+              case EPI_ACC: v.x = __fmul_rn(v.x, P.scale); v.y = __fmul_rn(v.y, P.scale); v.z = __fmul_rn(v.z, P.scale); v.w = __fmul_rn(v.w, P.scale); break;
+              case EPI_RELU: v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); break;
+              case EPI_TANH: v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); break;
+              case EPI_MISH: v.x = mishf_(v.x); v.y = mishf_(v.y); v.z = mishf_(v.z); v.w = mishf_(v.w); break;
+              case EPI_SILU: v.x = siluf_(v.x); v.y = siluf_(v.y); v.z = siluf_(v.z); v.w = siluf_(v.w); break;
+              default: break;
+            }
+            sts128(buf_sh + sw128(lane, qd), v);
           }
-          *cell = v;
         }
+        if (seg) { const long long t = clock64(); dbgacc[3] += t - ts0; ts0 = t; }
         fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          if (red_add) tma_reduce_add_3d(&tm_out, co0 + cb, T.q0 + quad * 32, T.g, buf);
-          else tma_store_3d(&tm_out, co0 + cb, T.q0 + quad * 32, T.g, buf);
-          tma_commit_group();
+        if (seg) { const long long t = clock64(); dbgacc[2] += t - ts0; ts0 = t; }
+        if (wb) {
+          if (leader && !has_res) {               // the NEXT block's buffer was last read by store j+1-NB: make sure
+            if (NB >= 4) tma_wait_group_read<2>();       // it is free before anybody passes the barrier below
+            else if (NB == 3) tma_wait_group_read<1>();
+            else tma_wait_group_read<0>();
+          }
+          named_bar_sync(2, 128);
+          if (leader) {
+            const uint8_t* blk = smem + S.stg + bi * V6_EBLK;
+            if (red_add) tma_reduce_add_3d(&tm_out, co0 + cb, T.q0, T.g, blk);
+            else tma_store_3d(&tm_out, co0 + cb, T.q0, T.g, blk);
+            tma_commit_group();
+          }
+        } else {
+          __syncwarp();
+          if (lane == 0) {
+            if (red_add) tma_reduce_add_3d(&tm_out, co0 + cb, T.q0 + quad * 32, T.g, buf);
+            else tma_store_3d(&tm_out, co0 + cb, T.q0 + quad * 32, T.g, buf);
+            tma_commit_group();
+          }
         }
+        if (seg) { const long long t = clock64(); dbgacc[7] += t - ts0; ts0 = t; }
       }
       if (dbg_on) dbgacc[6] += clock64() - t_epi0;
     }
-    if (lane == 0) tma_wait_group<0>();
+    if (leader) tma_wait_group<0>();
   } else {
     // =========================== epilogue warps (0..3) ===========================
     const int quad = warp;                       // TMEM lane quadrant this warp may access
@@ -514,17 +597,24 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
 }
 
 template <int BN>
-static void launch6(const TapConvParams& P, const CUtensorMap& tr, const CUtensorMap& to, int NI, int grid, size_t smem,
+static void launch6(const TapConvParams& P, const CUtensorMap& tr, const CUtensorMap& to, int RRA, int grid, size_t smem,
                     cudaStream_t st) {
-  if (NI <= 5) tcconv6_kernel<BN, 5><<<grid, V6_THREADS, smem, st>>>(P, tr, to);
-  else if (NI <= 6) tcconv6_kernel<BN, 6><<<grid, V6_THREADS, smem, st>>>(P, tr, to);
-  else tcconv6_kernel<BN, 10><<<grid, V6_THREADS, smem, st>>>(P, tr, to);
+  const int NI = cdiv(RRA, 32);
+  if (BN == 32 && P.Cin <= 32 && RRA <= 192) {   // narrow layers: 64 rows per pass, two register sets in flight
+    tcconv6_kernel<(BN == 32 ? 32 : 64), 3, true><<<grid, V6_THREADS, smem, st>>>(P, tr, to);
+    return;
+  }
+  if (NI <= 5) tcconv6_kernel<BN, 5, false><<<grid, V6_THREADS, smem, st>>>(P, tr, to);
+  else if (NI <= 6) tcconv6_kernel<BN, 6, false><<<grid, V6_THREADS, smem, st>>>(P, tr, to);
+  else tcconv6_kernel<BN, 10, false><<<grid, V6_THREADS, smem, st>>>(P, tr, to);
 }
 template <int BN>
 static void attrs6() {
-  AGPT_CUDA(cudaFuncSetAttribute(tcconv6_kernel<BN, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn6));
-  AGPT_CUDA(cudaFuncSetAttribute(tcconv6_kernel<BN, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn6));
-  AGPT_CUDA(cudaFuncSetAttribute(tcconv6_kernel<BN, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn6));
+  AGPT_CUDA(cudaFuncSetAttribute(tcconv6_kernel<BN, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn6));
+  AGPT_CUDA(cudaFuncSetAttribute(tcconv6_kernel<BN, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn6));
+  AGPT_CUDA(cudaFuncSetAttribute(tcconv6_kernel<BN, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn6));
+  if (BN == 32)
+    AGPT_CUDA(cudaFuncSetAttribute(tcconv6_kernel<32, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn6));
 }
 
 }  // namespace
@@ -547,17 +637,24 @@ static bool tcconv6_try(TapConvParams P, int BN, cudaStream_t st) {
   CUtensorMap tm_res, tm_out;
   memset(&tm_res, 0, sizeof(tm_res));
   memset(&tm_out, 0, sizeof(tm_out));
+  static int box_rows = 0;
+  if (!box_rows) { const char* e = getenv("AGPT_TC_EPIBOX"); box_rows = (e && atoi(e) == 32) ? 32 : 128; }
   bool tma = allow_tma && epi_ok && P.Wreal == 0;
-  if (tma) tma = tma_encode_rows(&tm_out, P.out, P.Cout, P.L, P.G, P.out_pitch, P.out_gstride, 32);
-  if (tma && has_res) tma = tma_encode_rows(&tm_res, P.res, P.Cout, P.L, P.G, P.res_pitch, P.res_gstride, 32);
-  const long fixed = 1024 /*align*/ + (4 * 256 * 4) /*cvs*/ + (2 * RRA * 4 + 2 * TC_ROWS * 4 + 48 * 8 + 64);
-  const long abytes = 2L * RRA * 128, wbytes = 2L * BN * 128;
+  if (tma) tma = tma_encode_rows(&tm_out, P.out, P.Cout, P.L, P.G, P.out_pitch, P.out_gstride, box_rows);
+  if (tma && has_res) tma = tma_encode_rows(&tm_res, P.res, P.Cout, P.L, P.G, P.res_pitch, P.res_gstride, box_rows);
+  if (tma && box_rows == 128) P.tc_flags |= (int)V6_FLAG_WBLK;
+  const long fixed = 1024 /*align*/ + (4 * 256 * 4) /*cvs*/ + (4 * RRA * 4 + 2 * TC_ROWS * 4 + 48 * 8 + 64);
+  // a weight stage holds tps taps (~32 KB): amortises the per-stage handshake on narrow layers
+  const int tps = std::max(1, std::min(P.ntaps, (int)(32768 / (2L * BN * 128))));
+  P.tc_tps = tps;
+  const long abytes = 2L * RRA * 128, wbytes = (long)tps * 2L * BN * 128;
+  const int stages_per_tile = P.tc_chunks_h * cdiv(P.ntaps, tps);
   int NA = 2, NB = 1, NW = 0;
   bool ok = false;
   for (int nb = tma ? 4 : 1; nb >= (tma ? 2 : 1) && !ok; --nb) {
     const long avail = (long)kMaxDyn6 - fixed - (long)nb * V6_EBLK - NA * abytes;
-    const int nw = (int)std::min<long>(MAX_NW6, avail / wbytes);
-    if (nw >= 3 || (nb == (tma ? 2 : 1) && nw >= 2)) { NB = nb; NW = nw; ok = true; }
+    const int nw = (int)std::min<long>(std::min(MAX_NW6, std::max(2, 2 * stages_per_tile)), avail / wbytes);
+    if (nw >= std::min(3, 2 * stages_per_tile) || (nb == (tma ? 2 : 1) && nw >= 2)) { NB = nb; NW = nw; ok = true; }
   }
   if (!ok) return false;      // a single operand buffer cannot overlap transform and MMA -> v5
   // without the TMA epilogue the 4 epilogue warps (LSU loads/stores, one 32-column block in flight) are the
@@ -570,7 +667,7 @@ static bool tcconv6_try(TapConvParams P, int BN, cudaStream_t st) {
   P.tc_na = NA; P.tc_nw = NW; P.tc_nb = NB;
   if (tma) P.tc_flags |= (int)V6_FLAG_TMA;
   Tc6Smem S;
-  tc6_layout(S, BN, RRA, NA, NW, NB);
+  tc6_layout(S, BN, RRA, NA, NW, NB, tps);
   const size_t smem = (size_t)S.total + 1024;
   if (smem > (size_t)kMaxDyn6) return false;
   const int Wv = P.Wreal > 0 ? P.Wreal + 1 : 0;
@@ -586,10 +683,10 @@ static bool tcconv6_try(TapConvParams P, int BN, cudaStream_t st) {
     attr_done_dev[dev & 63] = true;
   }
   const int grid = std::min(ntiles, sms_dev[dev & 63]);
-  if (BN == 256) launch6<256>(P, tm_res, tm_out, NI, grid, smem, st);
-  else if (BN == 128) launch6<128>(P, tm_res, tm_out, NI, grid, smem, st);
-  else if (BN == 64) launch6<64>(P, tm_res, tm_out, NI, grid, smem, st);
-  else launch6<32>(P, tm_res, tm_out, NI, grid, smem, st);
+  if (BN == 256) launch6<256>(P, tm_res, tm_out, RRA, grid, smem, st);
+  else if (BN == 128) launch6<128>(P, tm_res, tm_out, RRA, grid, smem, st);
+  else if (BN == 64) launch6<64>(P, tm_res, tm_out, RRA, grid, smem, st);
+  else launch6<32>(P, tm_res, tm_out, RRA, grid, smem, st);
   return true;
 }
 

@@ -35,6 +35,8 @@ void agpt_destroy(agpt_handle h);
  * saturation probe returning the measured TFLOP/s of the current device.       */
 int agpt_profile_enable(int on);
 int agpt_profile_collect(double ms[4], double flops[4], double bytes[4], long long launches[4]);
+/* dev tooling: one text line per recorded launch ("variant G L Cin Cout ntaps span epi Wreal ms flops"); returns bytes written or -1 */
+long agpt_profile_dump(char* out, long cap);
 double agpt_fma_peak_tflops(void);
 /* 1 (default): contractions run on tcgen05 tensor cores with 3xTF32 error compensation;
  * 0: fp32-FMA kernels only (bit-for-bit the round-1 numerics).                            */

@@ -176,7 +176,11 @@ allw = parallel.all_gather_rows(mine, counts=[3, 2])
 assert allw.shape == (5, 1, 7) and torch.equal(allw[:, 0, 0], torch.arange(5.0))
 eq = parallel.all_gather_rows(torch.full((2, 3), float(rank)))
 assert eq.shape == (4, 3) and eq[0, 0] == 0 and eq[3, 0] == 1
-print("rank", rank, "ok")
+print("rank", rank, "ok", flush=True)
+import torch.distributed as dist
+dist.barrier()
+dist.destroy_process_group()
+os._exit(0)        # skip interpreter teardown (gloo/TCPStore threads racing at exit made this flaky)
 """
 
 
