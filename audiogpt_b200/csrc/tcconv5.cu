@@ -381,6 +381,7 @@ void pack_h_weights(PackedConv& pc, const std::vector<float>& h) {
   pc.h_chunks = cdiv(pc.Cin, H_KCH);
   build_h_image(pc, h, pc.tc_bn, wscale, pc.w_h);
   if (pc.Cout % 256 == 0) build_h_image(pc, h, 256, wscale, pc.w_h256);
+  if (pc.tc_bn == 128) build_h_image(pc, h, 64, wscale, pc.w_h64);   // narrower tiles for launches that would not fill the SMs
 }
 
 // Try one tile width; returns false when it does not fit the shared-memory budget.
@@ -437,20 +438,41 @@ static bool tcconv5_try(TapConvParams P, int BN, cudaStream_t st) {
   return true;
 }
 
+// Tile width: the candidate (256 / native 128|64|32 / 64 for native-128 layers) with the smallest
+// waves x per-tile cost, where waves = ceil(tiles / SMs).  Per-tile cost relative to BN = 128 from the
+// micro-benchmarks (profiles/r1e_*): wider tiles amortise the activation operand, narrower ones fill the SMs.
+HTile pick_h_tile(const TapConvParams& P, int sms) {
+  static int allow256 = -1;
+  if (allow256 < 0) { const char* e = getenv("AGPT_TC_BN256"); allow256 = (e && e[0] == '0') ? 0 : 1; }
+  const int Wv = P.Wreal > 0 ? P.Wreal + 1 : 0;
+  const int Lv = Wv ? (P.L / P.Wreal) * Wv : P.L;
+  const long rt = (long)cdiv(Lv, TC_ROWS) * P.G;
+  auto cost = [](int bn) { return bn == 256 ? 1.7 : (bn == 128 ? 1.0 : (bn == 64 ? 0.62 : 0.45)); };
+  HTile best{P.tc_bn, P.w_h, rt * cdiv(P.Cout, P.tc_bn)};
+  double bs = (double)cdiv(best.ntiles, (long)sms) * cost(P.tc_bn);
+  auto consider = [&](int bn, const float* w) {
+    if (!w) return;
+    const long nt = rt * cdiv(P.Cout, bn);
+    const double sc = (double)cdiv(nt, (long)sms) * cost(bn);
+    if (sc < bs - 1e-9) { bs = sc; best = HTile{bn, w, nt}; }
+  };
+  if (allow256) consider(256, P.w_h256);
+  if (P.tc_bn == 128) consider(64, P.w_h64);
+  return best;
+}
+
 // returns false when the layer has no fp16 image or does not fit the shared-memory budget
 bool tcconv5_launch(TapConvParams P, cudaStream_t st) {
   if (!P.w_h) return false;
-  static int allow256 = -1;
-  if (allow256 < 0) { const char* e = getenv("AGPT_TC_BN256"); allow256 = (e && e[0] == '0') ? 0 : 1; }
-  if (allow256 && P.w_h256) {
-    const int Wv = P.Wreal > 0 ? P.Wreal + 1 : 0;
-    const int Lv = Wv ? (P.L / P.Wreal) * Wv : P.L;
-    const long ctas256 = (long)cdiv(Lv, TC_ROWS) * (P.Cout / 256) * P.G;
-    if (ctas256 >= 120) {
-      TapConvParams Q = P;
-      Q.w_h = P.w_h256;
-      if (tcconv5_try(Q, 256, st)) return true;
-    }
+  int dev = 0;
+  AGPT_CUDA(cudaGetDevice(&dev));
+  static int sms_dev[64] = {0};
+  if (!sms_dev[dev & 63]) AGPT_CUDA(cudaDeviceGetAttribute(&sms_dev[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+  const HTile c = pick_h_tile(P, sms_dev[dev & 63]);
+  if (c.bn != P.tc_bn) {
+    TapConvParams Q = P;
+    Q.w_h = c.w;
+    if (tcconv5_try(Q, c.bn, st)) return true;
   }
   return tcconv5_try(P, P.tc_bn, st);
 }

@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
       const int tl = k / nchunks, c = k - tl * nchunks;
       const TileId6 T = tile_of6((int)blockIdx.x + tl * (int)gridDim.x, nct, nrt);
       int* rowinfo = rowinfo_ring + (tl & 3) * RRA;
-      if (c == 0) {
+      if (c == 0 && Wv != 0) {
+        // (2-D layers only: a 1-D layer computes the row offset directly)
         // ring of 4 tiles: a slot is rewritten three tiles later; every thread passes this barrier only
         // after its own reads of the older tables were issued
         for (int i = xt; i < RRA; i += V6_NT) {
@@ -166,7 +167,12 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
       for (int u = 0; u < NI; ++u) {
         const int row = r0 + RSTR * u;
         int a = -1;
-        if (row < RRA) asm volatile("ld.shared.s32 %0, [%1];" : "=r"(a) : "r"(ri_sh + 4u * (uint32_t)row));
+        if (Wv == 0) {
+          const int qq = T.q0 + lo + row;
+          if (row < RRA && qq >= 0 && qq < Lv) a = qq * P.in_pitch;
+        } else if (row < RRA) {
+          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(a) : "r"(ri_sh + 4u * (uint32_t)row));
+        }
         const bool k0 = chok0 && (a >= 0), k1 = chok1 && (a >= 0);
         R.v0[u] = ldg_stream(k0 ? (ing + a + ch) : P.in);      // zero-select happens at use
         R.v1[u] = ldg_stream(k1 ? (ing + a + ch + 4) : P.in);
@@ -694,26 +700,20 @@ static bool tcconv6_try(TapConvParams P, int BN, cudaStream_t st) {
 // and v5's 8 transform+epilogue warps are at least as good).  Returns false -> caller uses v5.
 bool tcconv6_launch(TapConvParams P, cudaStream_t st, bool force) {
   if (!P.w_h) return false;
-  static int allow256 = -1;
-  if (allow256 < 0) { const char* e = getenv("AGPT_TC_BN256"); allow256 = (e && e[0] == '0') ? 0 : 1; }
-  int dev = 0, sms = 148;
+  int dev = 0;
   AGPT_CUDA(cudaGetDevice(&dev));
   static int sms_dev[64] = {0};
   if (!sms_dev[dev & 63]) AGPT_CUDA(cudaDeviceGetAttribute(&sms_dev[dev & 63], cudaDevAttrMultiProcessorCount, dev));
-  sms = sms_dev[dev & 63];
-  const int Wv = P.Wreal > 0 ? P.Wreal + 1 : 0;
-  const int Lv = Wv ? (P.L / P.Wreal) * Wv : P.L;
-  const long rt = (long)cdiv(Lv, TC_ROWS) * P.G;
-  if (allow256 && P.w_h256) {
-    const long ctas256 = rt * (P.Cout / 256);
-    if (ctas256 >= 120 && (force || ctas256 > sms)) {
-      TapConvParams Q = P;
-      Q.w_h = P.w_h256;
-      if (tcconv6_try(Q, 256, st)) return true;
-    }
+  const int sms = sms_dev[dev & 63];
+  const HTile c = pick_h_tile(P, sms);
+  if (!force && c.ntiles <= sms) return false;
+  if (c.bn != P.tc_bn) {
+    TapConvParams Q = P;
+    Q.w_h = c.w;
+    if (tcconv6_try(Q, c.bn, st)) return true;
+    const long ntiles = c.ntiles / cdiv(P.Cout, c.bn) * cdiv(P.Cout, P.tc_bn);
+    if (!force && ntiles <= sms) return false;
   }
-  const long ntiles = rt * cdiv(P.Cout, P.tc_bn);
-  if (!force && ntiles <= sms) return false;
   return tcconv6_try(P, P.tc_bn, st);
 }
 
