@@ -24,6 +24,7 @@ _INSTALL_MAP = {
     "ldm.modules.diffusionmodules.openaimodel": ("audiogpt_b200.ldm.modules.diffusionmodules.openaimodel",
                                                  ["UNetModel"]),
     "ldm.models.diffusion.ddim": ("audiogpt_b200.ldm.models.diffusion.ddim", ["DDIMSampler"]),
+    "vocoder.bigvgan.models": ("audiogpt_b200.vocoder.bigvgan.models", ["BigVGAN", "VocoderBigVGAN"]),
 }
 
 

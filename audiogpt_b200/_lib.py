@@ -31,7 +31,7 @@ class HifiganCfg(C.Structure):
         ("resblock_kernel_sizes", C.c_int * AGPT_MAX_RBK),
         ("resblock_num_dilations", C.c_int * AGPT_MAX_RBK),
         ("resblock_dilations", (C.c_int * AGPT_MAX_DIL) * AGPT_MAX_RBK),
-        ("use_nsf", C.c_int),
+        ("use_nsf", C.c_int), ("activation", C.c_int), ("snake_logscale", C.c_int),
     ]
 
 

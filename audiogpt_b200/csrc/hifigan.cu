@@ -64,6 +64,110 @@ __global__ void conv_post_kernel(const float* __restrict__ in, const float* __re
   }
 }
 
+// conv_post for the common C == 32 case: the block stages its (256 + 6) activated input rows ONCE in shared
+// memory with coalesced 128-bit loads (16-byte chunk c of row r at slot c ^ (r & 7): the row-per-thread reads
+// below are then bank-conflict free); same accumulation order as the generic kernel (bit-identical results).
+constexpr int CP_ROWS = 256;
+__global__ void __launch_bounds__(CP_ROWS) conv_post32_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, float* __restrict__ out,
+                                                               int L, int c_out, float slope) {
+  __shared__ float4 xs[(CP_ROWS + 6) * 8];
+  extern __shared__ float ws[];
+  for (int i = threadIdx.x; i < c_out * 7 * 32; i += CP_ROWS) ws[i] = w[i];
+  const int b = blockIdx.y;
+  const long p0 = (long)blockIdx.x * CP_ROWS;
+  const float4* ib = reinterpret_cast<const float4*>(in + (long)b * L * 32);
+  for (int i = threadIdx.x; i < (CP_ROWS + 6) * 8; i += CP_ROWS) {
+    const int r = i >> 3, c = i & 7;
+    const long q = p0 + r - 3;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q >= 0 && q < L) {
+      v = __ldg(ib + q * 8 + c);
+      v.x = lrelu(v.x, slope); v.y = lrelu(v.y, slope); v.z = lrelu(v.z, slope); v.w = lrelu(v.w, slope);
+    }
+    xs[r * 8 + (c ^ (r & 7))] = v;
+  }
+  __syncthreads();
+  const long p = p0 + threadIdx.x;
+  if (p >= L) return;
+  for (int oc = 0; oc < c_out; ++oc) {
+    float acc = bias[oc];
+    const float* wo = ws + oc * 7 * 32;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const long q = p + k - 3;
+      if (q < 0 || q >= L) continue;          // (zero rows contribute nothing; skipping keeps the generic kernel's order)
+      const int r = threadIdx.x + k;
+      const float* wk = wo + k * 32;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 x = xs[r * 8 + (c4 ^ (r & 7))];
+        acc = fmaf(x.x, wk[4 * c4 + 0], acc);
+        acc = fmaf(x.y, wk[4 * c4 + 1], acc);
+        acc = fmaf(x.z, wk[4 * c4 + 2], acc);
+        acc = fmaf(x.w, wk[4 * c4 + 3], acc);
+      }
+    }
+    out[((long)b * c_out + oc) * L + p] = tanhf(acc);
+  }
+}
+
+// Anti-aliased periodic activation of BigVGAN (Activation1d(Snake | SnakeBeta),
+// vocoder/bigvgan/alias_free_torch/act.py:22-27, resample.py:22-31, filter.py:80-90, activations.py:46-57,104-117):
+//   u = 2 * upfir2(replicate_pad(x, 5))[15:-15]          (12-tap Kaiser sinc, zero-stuffing stride 2: 6 taps per sample)
+//   s = u + inv_b[c] * sin^2(a[c] * u)
+//   y[t] = sum_k f[k] * replicate_pad(s, 5, 6)[2 t + k]   (stride-2 low-pass)
+// on channels-last rows [B][L][C].  One block: AA_TT output rows x 32 channels; the x tile, then the
+// activated 2x-rate samples are staged in shared memory so every sin() is evaluated once.
+struct AaFilter { float f[12]; };
+constexpr int AA_TT = 64;
+__global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                        const float* __restrict__ a, const float* __restrict__ inv_b,
+                                                        int L, int C, AaFilter F) {
+  __shared__ float xs[AA_TT + 12][32];
+  __shared__ float ss[2 * AA_TT + 10][32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.y * 32 + tx;
+  const int b = blockIdx.z;
+  const long t0 = (long)blockIdx.x * AA_TT;
+  const bool cok = c < C;
+  const float* xb = x + (long)b * L * C;
+  for (int r = ty; r < AA_TT + 12; r += 8) {
+    long t = t0 - 6 + r;
+    t = t < 0 ? 0 : (t > L - 1 ? L - 1 : t);
+    xs[r][tx] = cok ? __ldg(xb + t * C + c) : 0.f;
+  }
+  __syncthreads();
+  const float av = cok ? a[c] : 0.f, ib = cok ? inv_b[c] : 0.f;
+  for (int j = ty; j < 2 * AA_TT + 10; j += 8) {
+    long m = 2 * t0 - 5 + j;
+    m = m < 0 ? 0 : (m > 2 * (long)L - 1 ? 2 * (long)L - 1 : m);
+    const long n = m + 15;
+    float u = 0.f;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      if (((n - k) & 1) == 0) {
+        long xi = (n - k) / 2 - 5;                       // index into x (before the replicate pad of 5)
+        xi = xi < 0 ? 0 : (xi > L - 1 ? L - 1 : xi);
+        u = fmaf(F.f[k], xs[(int)(xi - (t0 - 6))][tx], u);
+      }
+    }
+    u *= 2.f;
+    const float sn = sinf(u * av);
+    ss[j][tx] = u + ib * (sn * sn);
+  }
+  __syncthreads();
+  float* yb = y + (long)b * L * C;
+  for (int r = ty; r < AA_TT; r += 8) {
+    const long t = t0 + r;
+    if (t >= L || !cok) continue;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc = fmaf(F.f[k], ss[2 * r + k][tx], acc);
+    yb[t * C + c] = acc;
+  }
+}
+
 // NSF excitation add: x[b][p][c] += bias[c] + sum_k w[c][k] * har[b][p*st - pad + k]   (hifigan.py:155-157)
 __global__ void nsf_add_kernel(float* __restrict__ x, const float* __restrict__ har, const float* __restrict__ w,
                                const float* __restrict__ bias, int L, int C, int Lh, int K, int st, int pad) {
@@ -81,10 +185,13 @@ __global__ void nsf_add_kernel(float* __restrict__ x, const float* __restrict__ 
   x[((long)b * L + p) * C + c] += acc;
 }
 
+struct SnakeW { DevBuf a, inv_b; };   // per-channel exp(alpha) (or alpha) and 1 / (beta + 1e-9)
+
 struct ResBlockW {
   int ks = 0;
   std::vector<int> dil;
   std::vector<PackedConv> c1, c2;  // c2 empty for ResBlock2
+  std::vector<SnakeW> act;          // BigVGAN: one anti-aliased snake per conv (AMPBlock1: 2 per pair)
 };
 
 struct NoiseConvW {
@@ -99,8 +206,10 @@ struct Hifigan : Handle {
   std::vector<ResBlockW> rbs;
   std::vector<NoiseConvW> noise;
   DevBuf post_w, post_b;
+  SnakeW act_post;                  // BigVGAN activation_post
+  AaFilter aaf;                     // the 12 Kaiser-sinc taps (state-dict buffer)
   int c_last = 0, hop = 1;
-  DevBuf melT, buf[6];
+  DevBuf melT, buf[6], sbuf;        // sbuf: activated conv input (BigVGAN only)
   DevBuf io_mel, io_wav, io_har;  // staging for the host-buffer entry point
   float* pin_mel = nullptr; float* pin_wav = nullptr; size_t pin_mel_n = 0, pin_wav_n = 0;
   cudaStream_t own_stream = nullptr;
@@ -124,6 +233,15 @@ struct Hifigan : Handle {
     for (auto& b : buf) b.ensure(mx);
     melT.ensure((size_t)B * T * cfg.n_mels);
     float *cur = buf[0].p, *acc = buf[1].p, *X = buf[2].p, *A = buf[3].p, *R0 = buf[4].p, *R1 = buf[5].p;
+    const bool big = cfg.activation != 0;          // BigVGAN: anti-aliased snake instead of leaky-relu
+    if (big) sbuf.ensure(mx);
+    float* S = sbuf.p;
+    auto snake = [&](const float* src, float* dst, long Lr, int Cr, const SnakeW& w) {
+      dim3 block(32, 8), grid(cdiv((int)Lr, AA_TT), cdiv(Cr, 32), B);
+      aa_snake_kernel<<<grid, block, 0, st>>>(src, dst, w.a.p, w.inv_b.p, (int)Lr, Cr, aaf);
+      count_launch(1);
+      AGPT_CUDA(cudaGetLastError());
+    };
 
     launch_cf_to_cl(mel, melT.p, B, cfg.n_mels, T, st);
     {
@@ -142,7 +260,7 @@ struct Hifigan : Handle {
         TapConvParams P = tapconv_params(ups[i], B, (int)L, 0, 1);
         P.in = cur; P.in_gstride = L * C; P.in_pitch = C;
         P.out = X; P.out_gstride = L * u * Co; P.out_pitch = u * Co;
-        P.pro = PRO_LRELU; P.slope = 0.1f; P.epi = EPI_BIAS;
+        P.pro = big ? PRO_NONE : PRO_LRELU; P.slope = 0.1f; P.epi = EPI_BIAS;   // BigVGAN upsamples x directly (models.py:184-186)
         tapconv_launch(P, st);
       }
       L *= u; C = Co;
@@ -164,18 +282,23 @@ struct Hifigan : Handle {
           float* dst = last ? acc : ((n & 1) ? R1 : R0);
           const float* conv_in = x;
           if (cfg.resblock_type == 1) {
+            if (big) snake(x, S, L, C, rb.act[2 * n]);      // xt = a1(x)   (AMPBlock1.forward, models.py:75-76)
             TapConvParams P = tapconv_params(rb.c1[n], B, (int)L, 0, rb.dil[n]);
-            P.in = x; P.in_gstride = gs; P.in_pitch = C;
+            P.in = big ? S : x; P.in_gstride = gs; P.in_pitch = C;
             P.out = A; P.out_gstride = gs; P.out_pitch = C;
-            P.pro = PRO_LRELU; P.slope = 0.1f; P.epi = EPI_BIAS;
+            P.pro = big ? PRO_NONE : PRO_LRELU; P.slope = 0.1f; P.epi = EPI_BIAS;
             tapconv_launch(P, st);
             conv_in = A;
+          }
+          if (big) {                                        // a2(xt) resp. AMPBlock2's a(x)
+            snake(conv_in, S, L, C, rb.act[cfg.resblock_type == 1 ? 2 * n + 1 : n]);
+            conv_in = S;
           }
           const PackedConv& pc = (cfg.resblock_type == 1) ? rb.c2[n] : rb.c1[n];
           TapConvParams P = tapconv_params(pc, B, (int)L, 0, (cfg.resblock_type == 1) ? 1 : rb.dil[n]);
           P.in = conv_in; P.in_gstride = gs; P.in_pitch = C;
           P.out = dst; P.out_gstride = gs; P.out_pitch = C;
-          P.pro = PRO_LRELU; P.slope = 0.1f;
+          P.pro = big ? PRO_NONE : PRO_LRELU; P.slope = 0.1f;
           P.res = x; P.res_gstride = gs; P.res_pitch = C;
           if (last) { P.epi = EPI_ACC; P.scale = inv_nk; P.accumulate = (j > 0); }
           else P.epi = EPI_RES;
@@ -189,7 +312,13 @@ struct Hifigan : Handle {
       const int threads = 256;
       dim3 grid(cdiv((int)L, threads), B);
       const size_t smem = (size_t)cfg.c_out * 7 * C * sizeof(float);
-      conv_post_kernel<<<grid, threads, smem, st>>>(cur, post_w.p, post_b.p, wav, (int)L, C, cfg.c_out, 0.01f);
+      const float* pin = cur;
+      float slope = 0.01f;                      // HiFi-GAN: F.leaky_relu default slope (hifigan.py:165)
+      if (big) { snake(cur, S, L, C, act_post); pin = S; slope = 1.f; }   // BigVGAN: activation_post, no leaky-relu
+      if (C == 32 && smem <= 8 * 1024)
+        conv_post32_kernel<<<grid, CP_ROWS, smem, st>>>(pin, post_w.p, post_b.p, wav, (int)L, cfg.c_out, slope);
+      else
+        conv_post_kernel<<<grid, threads, smem, st>>>(pin, post_w.p, post_b.p, wav, (int)L, C, cfg.c_out, slope);
       count_launch(1);
       AGPT_CUDA(cudaGetLastError());
     }
@@ -216,6 +345,19 @@ Handle* hifigan_create(const agpt_hifigan_cfg* cfg, const float* const* W, int n
     C /= 2; h->hop *= u;
   }
   h->c_last = C;
+  // BigVGAN (cfg.activation 1 = Snake, 2 = SnakeBeta): alpha [, beta] vectors follow each block's convs
+  auto load_snake = [&](SnakeW& sw, int ch) {
+    const float* al = next();
+    const float* be = (cfg->activation == 2) ? next() : al;
+    std::vector<float> a(ch), ib(ch);
+    for (int c = 0; c < ch; ++c) {
+      const float av = cfg->snake_logscale ? std::exp(al[c]) : al[c];
+      const float bv = cfg->snake_logscale ? std::exp(be[c]) : be[c];
+      a[c] = av;
+      ib[c] = 1.0f / (bv + 0.000000001f);
+    }
+    sw.a.upload(a); sw.inv_b.upload(ib);
+  };
   h->rbs.resize((size_t)nu * nk);
   C = C0;
   for (int i = 0; i < nu; ++i) {
@@ -232,8 +374,13 @@ Handle* hifigan_create(const agpt_hifigan_cfg* cfg, const float* const* W, int n
         rb.c2.resize(nd);
         for (int n = 0; n < nd; ++n) { const float* w = next(); const float* b = next(); pack_conv(rb.c2[n], w, b, C, C, rb.ks, false); }
       }
+      if (cfg->activation != 0) {
+        rb.act.resize(cfg->resblock_type == 1 ? 2 * nd : nd);
+        for (auto& a : rb.act) load_snake(a, C);
+      }
     }
   }
+  if (cfg->activation != 0) load_snake(h->act_post, C);
   {  // conv_post [c_out][C][7] -> [c_out][7][C]
     const float* w = next(); const float* b = next();
     std::vector<float> pw((size_t)cfg->c_out * 7 * C);
@@ -242,6 +389,10 @@ Handle* hifigan_create(const agpt_hifigan_cfg* cfg, const float* const* W, int n
         for (int k = 0; k < 7; ++k) pw[((size_t)oc * 7 + k) * C + c] = w[((size_t)oc * C + c) * 7 + k];
     h->post_w.upload(pw);
     h->post_b.upload(std::vector<float>(b, b + cfg->c_out));
+  }
+  if (cfg->activation != 0) {   // the Kaiser-sinc taps (identical upsample / downsample buffers of every Activation1d)
+    const float* f = next();
+    for (int k = 0; k < 12; ++k) h->aaf.f[k] = f[k];
   }
   if (cfg->use_nsf) {
     next(); next();  // m_source.l_linear.{weight,bias}: the source module stays on the host side (RNG)

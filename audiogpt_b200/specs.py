@@ -48,6 +48,19 @@ HIFIGAN_SMALL = dict(  # same topology, 8x narrower: CPU-second parity fixture
     audio_sample_rate=22050,
 )
 
+BIGVGAN_BASE = dict(  # BigVGAN-base 22 kHz / 80 band (the args.yml that ships with the Make-An-Audio vocoder
+    # checkpoint is download-only; topology of text_to_audio/Make_An_Audio/vocoder/bigvgan/models.py:133-203)
+    resblock="1", num_mels=80,
+    upsample_rates=[8, 8, 2, 2],
+    upsample_kernel_sizes=[16, 16, 4, 4],
+    upsample_initial_channel=512,
+    resblock_kernel_sizes=[3, 7, 11],
+    resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]],
+    activation="snakebeta", snake_logscale=True,
+)
+
+BIGVGAN_SMALL = dict(BIGVGAN_BASE, upsample_initial_channel=64)   # CPU-second parity fixture
+
 DIFFNET_BASE = dict(  # egs/egs_bases/svs/base.yaml:3-9, configs/tts/fs2.yaml:5
     in_dims=80, hidden_size=256, residual_layers=20, residual_channels=256,
     dilation_cycle_length=1,
@@ -139,6 +152,86 @@ def hifigan_param_shapes(h, c_out: int = 1, n_mels: int = 80) -> "OrderedDict[st
                 s[f"noise_convs.{i}.weight"] = (chans[i], 1, 1)
             s[f"noise_convs.{i}.bias"] = (chans[i],)
     return s
+
+
+def kaiser_sinc_filter12() -> torch.Tensor:
+    """The 12-tap Kaiser-windowed sinc low-pass (cutoff 0.25, half-width 0.3) that both halves of
+    Activation1d register as a buffer (vocoder/bigvgan/alias_free_torch/filter.py:19-47, resample.py:17-19,
+    38-41): shape [1, 1, 12]."""
+    ks, cutoff, half_width = 12, 0.25, 0.3
+    half = ks // 2
+    A = 2.285 * (half - 1) * math.pi * (4 * half_width) + 7.95
+    beta = 0.1102 * (A - 8.7) if A > 50.0 else (0.5842 * (A - 21) ** 0.4 + 0.07886 * (A - 21.0) if A >= 21.0 else 0.0)
+    window = torch.kaiser_window(ks, beta=beta, periodic=False)
+    time = torch.arange(-half, half) + 0.5
+    f = 2 * cutoff * window * torch.sinc(2 * cutoff * time)
+    f = f / f.sum()
+    return f.view(1, 1, ks)
+
+
+def bigvgan_param_shapes(h) -> "OrderedDict[str, Tuple[int, ...]]":
+    """Keys/shapes of BigVGAN.state_dict() after remove_weight_norm() (vocoder/bigvgan/models.py:133-175;
+    AMPBlock1 :29-83, AMPBlock2 :86-130; Activation1d buffers alias_free_torch/resample.py:19,41)."""
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    c0 = int(h["upsample_initial_channel"])
+    n_mels = int(h.get("num_mels", 80))
+    beta = str(h["activation"]) == "snakebeta"
+    s["conv_pre.weight"] = (c0, n_mels, 7)
+    s["conv_pre.bias"] = (c0,)
+    chans = hifigan_stage_channels(h)
+    for i, (u, k) in enumerate(zip(h["upsample_rates"], h["upsample_kernel_sizes"])):
+        s[f"ups.{i}.0.weight"] = (chans[i] * 2, chans[i], int(k))
+        s[f"ups.{i}.0.bias"] = (chans[i],)
+
+    def act(prefix, ch):
+        s[f"{prefix}.act.alpha"] = (ch,)
+        if beta:
+            s[f"{prefix}.act.beta"] = (ch,)
+        s[f"{prefix}.upsample.filter"] = (1, 1, 12)
+        s[f"{prefix}.downsample.lowpass.filter"] = (1, 1, 12)
+
+    nk = len(h["resblock_kernel_sizes"])
+    for i, ch in enumerate(chans):
+        for j, (ks, dil) in enumerate(zip(h["resblock_kernel_sizes"], h["resblock_dilation_sizes"])):
+            p = f"resblocks.{i * nk + j}"
+            if str(h["resblock"]) == "1":
+                for n in range(len(dil)):
+                    s[f"{p}.convs1.{n}.weight"] = (ch, ch, int(ks))
+                    s[f"{p}.convs1.{n}.bias"] = (ch,)
+                for n in range(len(dil)):
+                    s[f"{p}.convs2.{n}.weight"] = (ch, ch, int(ks))
+                    s[f"{p}.convs2.{n}.bias"] = (ch,)
+                for m in range(2 * len(dil)):
+                    act(f"{p}.activations.{m}", ch)
+            else:
+                for n in range(len(dil)):
+                    s[f"{p}.convs.{n}.weight"] = (ch, ch, int(ks))
+                    s[f"{p}.convs.{n}.bias"] = (ch,)
+                for m in range(len(dil)):
+                    act(f"{p}.activations.{m}", ch)
+    act("activation_post", chans[-1])
+    s["conv_post.weight"] = (1, chans[-1], 7)
+    s["conv_post.bias"] = (1,)
+    return s
+
+
+def synth_bigvgan(h, seed: int = 4321):
+    """Seeded BigVGAN weights: convs as synth_hifigan; snake alpha/beta ~ N(0, 0.3^2) (log scale) or
+    1 + 0.3 N (linear scale); the filter buffers hold the Kaiser-sinc taps."""
+    shapes = bigvgan_param_shapes(h)
+    # gain 0.7: the snake activations do not attenuate like leaky-relu; keeps tanh unsaturated (rms ~0.1)
+    sd = synth_state_dict(shapes, seed, gain=0.7, gains={"conv_post.weight": 0.143})
+    logscale = bool(h.get("snake_logscale", False))
+    filt = kaiser_sinc_filter12()
+    for idx, key in enumerate(shapes):
+        if key.endswith(".filter"):
+            sd[key] = filt.clone()
+        elif key.endswith(".act.alpha") or key.endswith(".act.beta"):
+            g = torch.Generator(device="cpu")
+            g.manual_seed(int(seed) * 7919 + idx)
+            t = 0.3 * torch.randn(shapes[key], generator=g, dtype=torch.float32)
+            sd[key] = t if logscale else (1.0 + t).abs() + 0.1
+    return sd
 
 
 # --------------------------------------------------------------------------

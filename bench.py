@@ -396,6 +396,28 @@ def extra_metrics(dev):
     out["diffsinger_c3_utt_per_s"] = Bc / dt
     out["diffsinger_c3_seconds_16utt_100steps"] = dt
     out["diffsinger_c3_tflops"] = 26.44e6 * Bc * Tc * 100 / dt / 1e12
+    del net, gd
+    torch.cuda.empty_cache()
+    # --- BigVGAN ("next" row 8f-2: the vocoder Make-An-Audio actually dispatches), base 22 kHz / 80-band topology
+    from audiogpt_b200.vocoder.bigvgan.models import BigVGAN
+    hb = specs.BIGVGAN_BASE
+    bv = BigVGAN(hb)
+    bv.load_state_dict(specs.synth_bigvgan(hb, 4321), strict=True)
+    bv = bv.eval().to(dev)
+    Bb, Tb = 8, 400
+    melb = specs.synth_tensor((Bb, 80, Tb), seed=9, scale=2.0, shift=-4.0).to(dev)
+    for _ in range(2):
+        bv(melb)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        wb = bv(melb)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    msb = e0.elapsed_time(e1) / 3
+    out["bigvgan_base_frames_per_s"] = Bb * Tb / (msb * 1e-3)
+    out["bigvgan_base_ms_8x400"] = msb
+    out["bigvgan_base_finite"] = bool(torch.isfinite(wb).all().item())
     return out
 
 

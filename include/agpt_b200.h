@@ -71,6 +71,14 @@ typedef struct {
   int resblock_num_dilations[AGPT_MAX_RBK];
   int resblock_dilations[AGPT_MAX_RBK][AGPT_MAX_DIL];
   int use_nsf;                 /* h['use_pitch_embed']: noise_convs present (hifigan.py:111-132) */
+  /* BigVGAN (text_to_audio/Make_An_Audio/vocoder/bigvgan/models.py:133-203) is the same generator with
+   * anti-aliased periodic activations (Activation1d(Snake|SnakeBeta)) instead of leaky-relu:
+   * activation 0 = leaky-relu (HiFi-GAN), 1 = 'snake', 2 = 'snakebeta'; snake_logscale = h.snake_logscale.
+   * With activation != 0 the weight list is: conv_pre w,b; ups w,b ...; per resblock: convs1 w,b x nd,
+   * convs2 w,b x nd, then alpha[, beta] for activations.0 .. (2 nd - 1); activation_post alpha[, beta];
+   * conv_post w,b; the 12 filter taps (Activation1d's registered buffer).                          */
+  int activation;
+  int snake_logscale;
 } agpt_hifigan_cfg;
 
 /* host_weights: fp32 HOST arrays in the key order of

@@ -258,6 +258,7 @@ def import_ldm():
 
     lc.ListConfig = ListConfig
     oc.listconfig = lc
+    oc.OmegaConf = MagicMock()     # vocoder/bigvgan/models.py imports the name (used only by VocoderBigVGAN.__init__)
     sys.modules.setdefault("omegaconf", oc)
     sys.modules.setdefault("omegaconf.listconfig", lc)
     # the NeuralSeq tree also has a top-level 'modules'/'utils'; make sure ldm wins its own names
@@ -348,8 +349,30 @@ def golden_ldm():
     save("ldm_txt2audio", eps_pair=ef, ddim100_first4=img)
 
 
+def golden_bigvgan():
+    """BigVGAN generator of Make-An-Audio's vocoder (vocoder/bigvgan/models.py:133-203), small config."""
+    from vocoder.bigvgan.models import BigVGAN
+
+    class AttrDict(dict):
+        __getattr__ = dict.__getitem__
+
+    h = specs.BIGVGAN_SMALL
+    sd = specs.synth_bigvgan(h, 4321)
+    m = BigVGAN(AttrDict(h))
+    m.remove_weight_norm()
+    missing = m.load_state_dict(sd, strict=True)
+    print("bigvgan load:", missing)
+    m.eval()
+    mel = specs.synth_tensor((2, 80, 20), seed=5, scale=2.0, shift=-4.0)
+    with torch.no_grad():
+        wav = m(mel)
+        wav1 = m(mel[:1, :, :7])      # ragged / shorter than the replicate pads
+    print("bigvgan small wav rms", wav.pow(2).mean().sqrt().item(), "absmax", wav.abs().max().item())
+    save("bigvgan_small", wav=wav, wav_t7=wav1)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["hifigan", "diffusion", "ldm"]
+    which = sys.argv[1:] or ["hifigan", "diffusion", "ldm", "bigvgan"]
     if "hifigan" in which or "diffusion" in which:
         import_neuralseq()
         cwd = os.getcwd()
@@ -369,3 +392,10 @@ if __name__ == "__main__":
             sys.path.remove(os.path.join(REF, "NeuralSeq"))
         import_ldm()
         golden_ldm()
+    if "bigvgan" in which:
+        for k in [k for k in sys.modules if k.split(".")[0] in ("modules", "utils", "vocoders", "tasks")]:
+            del sys.modules[k]
+        if os.path.join(REF, "NeuralSeq") in sys.path:
+            sys.path.remove(os.path.join(REF, "NeuralSeq"))
+        import_ldm()
+        golden_bigvgan()

@@ -63,12 +63,13 @@ def test_install_aliases_reference_module_names():
             "from ldm.modules.diffusionmodules.openaimodel import UNetModel as U; "
             "from ldm.models.diffusion.ddim import DDIMSampler as D; "
             "from modules.diff.shallow_diffusion_tts import GaussianDiffusion as G; "
+            "from vocoder.bigvgan.models import BigVGAN as V; assert V.__module__.startswith('audiogpt_b200'); "
             "assert H.__module__.startswith('audiogpt_b200') and U.__module__.startswith('audiogpt_b200'); "
             "assert D.__module__.startswith('audiogpt_b200') and G.__module__.startswith('audiogpt_b200'); "
             "print(len(p))") % ROOT
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stderr
-    assert r.stdout.strip() == "6"
+    assert r.stdout.strip() == "7"
 
 
 def test_param_tables_match_survey_counts():

@@ -158,3 +158,21 @@ def test_unet_txt2audio_forward():
     fn = lambda x, t, c: lr.unet_forward(sd, cfg, x, t, c)
     out = lr.ddim_sample(fn, sch["alphas_cumprod"], 100, xf, cf, ucf, 1.5, steps_limit=4)
     assert rel_rmse(out, g["ddim100_first4"]) < 1e-4
+
+
+def test_bigvgan_small():
+    """oracle/bigvgan_ref.py == the reference's BigVGAN module (fixture made by make_golden.py bigvgan)."""
+    from oracle import bigvgan_ref as br
+    g = load_golden("bigvgan_small")
+    h = specs.BIGVGAN_SMALL
+    sd = specs.synth_bigvgan(h, 4321)
+    mel = specs.synth_tensor((2, 80, 20), seed=5, scale=2.0, shift=-4.0)
+    wav = br.bigvgan_forward(sd, h, mel)
+    assert wav.shape == (2, 1, 20 * 256)
+    assert rel_rmse(wav, g["wav"]) < 1e-6
+    wav7 = br.bigvgan_forward(sd, h, mel[:1, :, :7])
+    assert rel_rmse(wav7, g["wav_t7"]) < 1e-6
+    assert float(np.abs(g["wav"]).max()) < 0.9           # tanh not saturated: the comparison is meaningful
+    # the filter buffers of the state dict are the published Kaiser-sinc taps
+    f = specs.kaiser_sinc_filter12().reshape(-1)
+    assert abs(float(f.sum()) - 1.0) < 1e-6 and torch.allclose(f, f.flip(0), atol=1e-7)
