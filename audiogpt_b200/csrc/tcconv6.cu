@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
   const int nct = (P.Cout + BN - 1) / BN, nrt = (Lv + TC_ROWS - 1) / TC_ROWS;
   const int ntiles = nct * nrt * P.G;
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  constexpr uint32_t TMEM_COLS = (BN <= 64) ? 512 : 2 * BN;   // (BN <= 64: room for the split-chain experiment, flag 512)
+  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;    // two accumulators
 
   if (tid == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], V6_NT); mbar_init(&a_empty[i], 1); }
@@ -324,8 +324,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
     // (reduce-add when the layer accumulates into its output).  No LSU global traffic, no cross-warp sync.
     const int quad = warp;
     const int NB = P.tc_nb;
-    const bool slack2 = (P.tc_flags & 256) && NB >= 3;   // allow 2 stores in flight (residual look-ahead NB-3) instead of 1 (NB-2)
-    const int LA = slack2 ? NB - 3 : NB - 2;
+    const int LA = NB - 2;                                  // residual look-ahead in blocks (one store may be in flight)
     const bool has_res = (P.epi == EPI_RES || P.epi == EPI_ACC) && P.res != nullptr;
     const bool red_add = (P.epi == EPI_ACC) && P.accumulate;
     // whole-block mode (default): ONE tensor-map op moves a [128 rows x 32 columns] block for all four warps
@@ -378,12 +377,9 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
 #pragma unroll 1
       for (int cb = 0; cb < BN; cb += 32, ++j) {
         const int bi = j % NB;
-        const bool seg = dbg_on && (P.tc_flags & 4);
-        long long ts0 = seg ? clock64() : 0;
         if (leader) {
           if (has_res) {
-            if (slack2) tma_wait_group_read<2>();  // store j-3 (resp. j-2) has left its buffer == the buffer of block j+LA
-            else tma_wait_group_read<1>();
+            tma_wait_group_read<1>();             // store j-2 has left its buffer == the buffer of block j+LA
             if (j + LA < total_blk) issue_load(j + LA);
           } else if (!wb) {                       // buffer bi was last used by store j-NB
             if (NB >= 4) tma_wait_group_read<3>();
@@ -392,13 +388,11 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
           }
         }
         if (!wb) __syncwarp();
-        if (seg) { const long long t = clock64(); dbgacc[1] += t - ts0; ts0 = t; }
         if (!acc_ready) {
           DBG_WAIT6(5, mbar_wait(&acc_full[acc], (uint32_t)((tl >> 1) & 1)));
           tc_fence_after();
           acc_ready = true;
           t_epi0 = dbg_on ? clock64() : 0;
-          if (seg) ts0 = clock64();
         }
         uint32_t rg[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + cb);
@@ -416,7 +410,6 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
           tc_fence_before();
           mbar_arrive(&acc_empty[acc]);
         }
-        if (seg) { const long long t = clock64(); dbgacc[2] += t - ts0; ts0 = t; }
         if (has_res) DBG_WAIT6(4, mbar_wait(&efull[bi], (uint32_t)((j / NB) & 1)));
         uint8_t* buf = ebuf + bi * V6_EBLK;
         // two halves of four 16-byte cells: all shared-memory loads of a half are issued before any store
@@ -449,9 +442,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
             sts128(buf_sh + sw128(lane, qd), v);
           }
         }
-        if (seg) { const long long t = clock64(); dbgacc[3] += t - ts0; ts0 = t; }
         fence_proxy_async();
-        if (seg) { const long long t = clock64(); dbgacc[2] += t - ts0; ts0 = t; }
         if (wb) {
           if (leader && !has_res) {               // the NEXT block's buffer was last read by store j+1-NB: make sure
             if (NB >= 4) tma_wait_group_read<2>();       // it is free before anybody passes the barrier below
@@ -473,7 +464,6 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
             tma_commit_group();
           }
         }
-        if (seg) { const long long t = clock64(); dbgacc[7] += t - ts0; ts0 = t; }
       }
       if (dbg_on) dbgacc[6] += clock64() - t_epi0;
     }
@@ -531,7 +521,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
           if (pp[i] >= 0) prea[i] = epi_load_a(P, T.g, pp[i], co0 + cb + 4 * (idx & 7));
         }
       };
-      if (!(P.tc_flags & 8)) load_block(0);       // global reads in flight while the tile is still accumulating
+      load_block(0);                              // global reads in flight while the tile is still accumulating
       DBG_WAIT6(5, mbar_wait(&acc_full[acc], (uint32_t)((tl >> 1) & 1)));
       tc_fence_after();
       const long long t_epi0 = dbg_on ? clock64() : 0;
@@ -555,9 +545,6 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
           tc_fence_before();
           mbar_arrive(&acc_empty[acc]);
         }
-        if (P.tc_flags & 8) continue;             // experiment: no staging, no global traffic
-        const bool seg = dbg_on && (P.tc_flags & 4);
-        long long ts0 = seg ? clock64() : 0;
         __syncwarp();                             // the previous block's staging rows have been consumed
 #pragma unroll
         for (int qd = 0; qd < 8; ++qd)
@@ -565,10 +552,8 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
               make_float4(__uint_as_float(rg[4 * qd]) * dsc, __uint_as_float(rg[4 * qd + 1]) * dsc,
                           __uint_as_float(rg[4 * qd + 2]) * dsc, __uint_as_float(rg[4 * qd + 3]) * dsc);
         __syncwarp();
-        if (seg) { const long long t = clock64(); dbgacc[1] += t - ts0; ts0 = t; }
         const int jc = lane & 7;                  // all 8 items of this lane share the 4-channel group
         float4 cv = epi_colvec(P, T.g, co0 + cb + 4 * jc);
-        if (seg) { if (cv.x == 123.456f) cv.y += 1.f; const long long t = clock64(); dbgacc[2] += t - ts0; ts0 = t; }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int row = (lane >> 3) + 4 * i;
@@ -579,19 +564,15 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
             epi_store_cv(P, T.g, pp[i], co0 + cb + 4 * jc, *reinterpret_cast<const float4*>(stg + sw128(row, jc)), e, cv);
           }
         }
-        if (seg) { const long long t = clock64(); dbgacc[3] += t - ts0; ts0 = t; }
         if (cb + 32 < BN) load_block(cb + 32);
-        if (seg) { const long long t = clock64(); dbgacc[7] += t - ts0; ts0 = t; }
       }
       if (dbg_on) dbgacc[6] += clock64() - t_epi0;
     }
   }
 
   if (dbg_on) {
-    const bool segm = (P.tc_flags & 4) != 0;     // experiment: slots 1,2,3,7 = epilogue segments (stage, colvec, items, next loads)
-    if (!segm && warp == 4 && lane == 0) { dbg[1] = dbgacc[1]; dbg[2] = dbgacc[2]; dbg[3] = dbgacc[3]; }
-    if (!segm && warp == 5 && lane == 0) dbg[7] = dbgacc[7];
-    if (segm && tid == 0) { dbg[1] = dbgacc[1]; dbg[2] = dbgacc[2]; dbg[3] = dbgacc[3]; dbg[7] = dbgacc[7]; }
+    if (warp == 4 && lane == 0) { dbg[1] = dbgacc[1]; dbg[2] = dbgacc[2]; dbg[3] = dbgacc[3]; }
+    if (warp == 5 && lane == 0) dbg[7] = dbgacc[7];
     if (tid == 0) { dbg[4] = dbgacc[4]; dbg[5] = dbgacc[5]; dbg[6] = dbgacc[6]; }   // [4]: epilogue time inside tcgen05.ld + wait::ld
   }
   tc_fence_before();
