@@ -129,28 +129,27 @@ __global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.y * 32 + tx;
   const int b = blockIdx.z;
-  const long t0 = (long)blockIdx.x * AA_TT;
+  const int t0 = blockIdx.x * AA_TT;
   const bool cok = c < C;
   const float* xb = x + (long)b * L * C;
   for (int r = ty; r < AA_TT + 12; r += 8) {
-    long t = t0 - 6 + r;
-    t = t < 0 ? 0 : (t > L - 1 ? L - 1 : t);
-    xs[r][tx] = cok ? __ldg(xb + t * C + c) : 0.f;
+    const int t = min(max(t0 - 6 + r, 0), L - 1);
+    xs[r][tx] = cok ? __ldg(xb + (long)t * C + c) : 0.f;
   }
   __syncthreads();
   const float av = cok ? a[c] : 0.f, ib = cok ? inv_b[c] : 0.f;
+  // up-FIR: sample m = 2 i + r of the zero-stuffed convolution touches the 6 taps k = (n & 1) + 2 q, n = m + 15,
+  // applied to x[(n >> 1) - 5 - q] (replicate-clamped); taps are visited in ascending k like a direct convolution
   for (int j = ty; j < 2 * AA_TT + 10; j += 8) {
-    long m = 2 * t0 - 5 + j;
-    m = m < 0 ? 0 : (m > 2 * (long)L - 1 ? 2 * (long)L - 1 : m);
-    const long n = m + 15;
+    const int m = min(max(2 * t0 - 5 + j, 0), 2 * L - 1);
+    const int n = m + 15;
+    const bool odd = (n & 1) != 0;
+    const int base = (n >> 1) - 5;
     float u = 0.f;
 #pragma unroll
-    for (int k = 0; k < 12; ++k) {
-      if (((n - k) & 1) == 0) {
-        long xi = (n - k) / 2 - 5;                       // index into x (before the replicate pad of 5)
-        xi = xi < 0 ? 0 : (xi > L - 1 ? L - 1 : xi);
-        u = fmaf(F.f[k], xs[(int)(xi - (t0 - 6))][tx], u);
-      }
+    for (int q = 0; q < 6; ++q) {
+      const int xi = min(max(base - q, 0), L - 1) - (t0 - 6);
+      u = fmaf(odd ? F.f[2 * q + 1] : F.f[2 * q], xs[xi][tx], u);
     }
     u *= 2.f;
     const float sn = sinf(u * av);
@@ -159,12 +158,12 @@ __global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__
   __syncthreads();
   float* yb = y + (long)b * L * C;
   for (int r = ty; r < AA_TT; r += 8) {
-    const long t = t0 + r;
+    const int t = t0 + r;
     if (t >= L || !cok) continue;
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < 12; ++k) acc = fmaf(F.f[k], ss[2 * r + k][tx], acc);
-    yb[t * C + c] = acc;
+    yb[(long)t * C + c] = acc;
   }
 }
 
