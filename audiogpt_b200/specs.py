@@ -61,6 +61,13 @@ BIGVGAN_BASE = dict(  # BigVGAN-base 22 kHz / 80 band (the args.yml that ships w
 
 BIGVGAN_SMALL = dict(BIGVGAN_BASE, upsample_initial_channel=64)   # CPU-second parity fixture
 
+VAE_TXT2AUDIO = dict(  # first_stage_config.ddconfig, configs/text_to_audio/txt2audio_args.yaml:52-68
+    embed_dim=4, z_channels=4, resolution=848, in_channels=1, out_ch=1, ch=128, ch_mult=[1, 2, 2, 4],
+    num_res_blocks=2, attn_resolutions=[106, 212], dropout=0.0, double_z=True,
+)
+
+VAE_SMALL = dict(VAE_TXT2AUDIO, ch=32)   # same topology (attention at the same levels), 4x narrower
+
 DIFFNET_BASE = dict(  # egs/egs_bases/svs/base.yaml:3-9, configs/tts/fs2.yaml:5
     in_dims=80, hidden_size=256, residual_layers=20, residual_channels=256,
     dilation_cycle_length=1,
@@ -456,6 +463,74 @@ def synth_hifigan(h, seed: int = 1234, c_out: int = 1):
     """Seeded generator weights; conv_post is scaled down so that tanh is not
     saturated (pre-tanh rms ~0.35) and waveform RMSE is a meaningful metric."""
     return synth_state_dict(hifigan_param_shapes(h, c_out), seed, gains={"conv_post.weight": 0.35})
+
+
+def vae_decoder_plan(cfg):
+    """Block list of ldm Decoder.__init__ (ldm/modules/diffusionmodules/model.py:462-536): returns
+    (block_in at the bottom, [(level, [(cin, cout, has_attn), ...], has_upsample), ...] in execution order)."""
+    ch, mult = int(cfg["ch"]), list(cfg["ch_mult"])
+    nres = len(mult)
+    block_in = ch * mult[-1]
+    curr_res = int(cfg["resolution"]) // 2 ** (nres - 1)
+    levels = []
+    bi = block_in
+    for i_level in reversed(range(nres)):
+        bo = ch * mult[i_level]
+        blocks = []
+        for _ in range(int(cfg["num_res_blocks"]) + 1):
+            blocks.append((bi, bo, curr_res in cfg["attn_resolutions"]))
+            bi = bo
+        up = i_level != 0
+        levels.append((i_level, blocks, up))
+        if up:
+            curr_res *= 2
+    return block_in, levels
+
+
+def vae_decoder_param_shapes(cfg) -> "OrderedDict[str, Tuple[int, ...]]":
+    """post_quant_conv (ldm/models/autoencoder.py:307) + decoder.* (model.py:462-536) of AutoencoderKL."""
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    zc, ed = int(cfg["z_channels"]), int(cfg["embed_dim"])
+    s["post_quant_conv.weight"] = (zc, ed, 1, 1)
+    s["post_quant_conv.bias"] = (zc,)
+    block_in, levels = vae_decoder_plan(cfg)
+
+    def res(p, cin, cout):
+        s[f"{p}.norm1.weight"] = (cin,); s[f"{p}.norm1.bias"] = (cin,)
+        s[f"{p}.conv1.weight"] = (cout, cin, 3, 3); s[f"{p}.conv1.bias"] = (cout,)
+        s[f"{p}.norm2.weight"] = (cout,); s[f"{p}.norm2.bias"] = (cout,)
+        s[f"{p}.conv2.weight"] = (cout, cout, 3, 3); s[f"{p}.conv2.bias"] = (cout,)
+        if cin != cout:
+            s[f"{p}.nin_shortcut.weight"] = (cout, cin, 1, 1); s[f"{p}.nin_shortcut.bias"] = (cout,)
+
+    def attn(p, c):
+        s[f"{p}.norm.weight"] = (c,); s[f"{p}.norm.bias"] = (c,)
+        for n in ("q", "k", "v", "proj_out"):
+            s[f"{p}.{n}.weight"] = (c, c, 1, 1); s[f"{p}.{n}.bias"] = (c,)
+
+    s["decoder.conv_in.weight"] = (block_in, zc, 3, 3)
+    s["decoder.conv_in.bias"] = (block_in,)
+    res("decoder.mid.block_1", block_in, block_in)
+    attn("decoder.mid.attn_1", block_in)
+    res("decoder.mid.block_2", block_in, block_in)
+    last = block_in
+    for i_level, blocks, up in levels:
+        for j, (cin, cout, has_attn) in enumerate(blocks):
+            res(f"decoder.up.{i_level}.block.{j}", cin, cout)
+            if has_attn:
+                attn(f"decoder.up.{i_level}.attn.{j}", cout)
+            last = cout
+        if up:
+            s[f"decoder.up.{i_level}.upsample.conv.weight"] = (last, last, 3, 3)
+            s[f"decoder.up.{i_level}.upsample.conv.bias"] = (last,)
+    s["decoder.norm_out.weight"] = (last,); s["decoder.norm_out.bias"] = (last,)
+    s["decoder.conv_out.weight"] = (int(cfg["out_ch"]), last, 3, 3)
+    s["decoder.conv_out.bias"] = (int(cfg["out_ch"]),)
+    return s
+
+
+def synth_vae_decoder(cfg, seed: int = 5150):
+    return synth_state_dict(vae_decoder_param_shapes(cfg), seed, convtranspose_prefixes=())
 
 
 def synth_diffnet(cfg, seed: int = 2024):

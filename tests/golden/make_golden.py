@@ -371,8 +371,33 @@ def golden_bigvgan():
     save("bigvgan_small", wav=wav, wav_t7=wav1)
 
 
+def golden_vae():
+    """AutoencoderKL.decode = post_quant_conv -> Decoder (ldm/models/autoencoder.py:351-354; the LightningModule
+    itself needs pytorch_lightning/taming, so the two sub-modules it calls are instantiated directly)."""
+    from ldm.modules.diffusionmodules.model import Decoder
+
+    def run(cfg, seed, z):
+        sd = specs.synth_vae_decoder(cfg, seed)
+        dec = Decoder(**{k: v for k, v in cfg.items() if k != "embed_dim"})
+        print("vae decoder load:", dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items()
+                                                        if k.startswith("decoder.")}, strict=True))
+        pq = torch.nn.Conv2d(cfg["embed_dim"], cfg["z_channels"], 1)
+        pq.load_state_dict({"weight": sd["post_quant_conv.weight"], "bias": sd["post_quant_conv.bias"]})
+        dec.eval()
+        with torch.no_grad():
+            return dec(pq(z))
+
+    z = specs.synth_tensor((2, 4, 10, 78), seed=3)
+    ys = run(specs.VAE_SMALL, 5150, z)
+    print("vae small out rms", ys.pow(2).mean().sqrt().item(), tuple(ys.shape))
+    save("vae_small", mel=ys[:, :, ::2, ::3], stats=stats(ys))
+    yf = run(specs.VAE_TXT2AUDIO, 5150, z[:1])
+    print("vae txt2audio out rms", yf.pow(2).mean().sqrt().item(), tuple(yf.shape))
+    save("vae_txt2audio", mel=yf[:, :, ::2, ::3], stats=stats(yf))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["hifigan", "diffusion", "ldm", "bigvgan"]
+    which = sys.argv[1:] or ["hifigan", "diffusion", "ldm", "bigvgan", "vae"]
     if "hifigan" in which or "diffusion" in which:
         import_neuralseq()
         cwd = os.getcwd()
@@ -399,3 +424,10 @@ if __name__ == "__main__":
             sys.path.remove(os.path.join(REF, "NeuralSeq"))
         import_ldm()
         golden_bigvgan()
+    if "vae" in which:
+        for k in [k for k in sys.modules if k.split(".")[0] in ("modules", "utils", "vocoders", "tasks")]:
+            del sys.modules[k]
+        if os.path.join(REF, "NeuralSeq") in sys.path:
+            sys.path.remove(os.path.join(REF, "NeuralSeq"))
+        import_ldm()
+        golden_vae()

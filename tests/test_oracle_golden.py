@@ -176,3 +176,21 @@ def test_bigvgan_small():
     # the filter buffers of the state dict are the published Kaiser-sinc taps
     f = specs.kaiser_sinc_filter12().reshape(-1)
     assert abs(float(f.sum()) - 1.0) < 1e-6 and torch.allclose(f, f.flip(0), atol=1e-7)
+
+
+def test_vae_decode_small_and_txt2audio():
+    """oracle/vae_ref.py == the reference's Decoder + post_quant_conv (fixtures hold a strided
+    view and the global sum / |sum| / sum of squares of the full 80 x 624 output)."""
+    from oracle import vae_ref as vr
+    z = specs.synth_tensor((2, 4, 10, 78), seed=3)
+    for name, cfg, zz in (("vae_small", specs.VAE_SMALL, z), ("vae_txt2audio", specs.VAE_TXT2AUDIO, z[:1])):
+        g = load_golden(name)
+        y = vr.vae_decode(specs.synth_vae_decoder(cfg, 5150), cfg, zz)
+        assert y.shape == (zz.shape[0], 1, 80, 624)
+        assert rel_rmse(y[:, :, ::2, ::3], g["mel"]) < 2e-5
+        yd = y.double()
+        st = np.array([yd.sum().item(), yd.abs().sum().item(), (yd * yd).sum().item()])
+        assert np.allclose(st[1:], g["stats"][1:], rtol=1e-4)
+    n = sum(int(np.prod(s)) for s in specs.vae_decoder_param_shapes(specs.VAE_TXT2AUDIO).values())
+    assert abs(n / 41.0e6 - 1) < 0.01                                  # 41 M params (SURVEY 8f)
+    assert abs(vr.vae_decode_flops(specs.VAE_TXT2AUDIO, 10, 78) / 392.9e9 - 1) < 0.01   # 392.9 GFLOP / clip
