@@ -199,3 +199,29 @@ def test_world_size_2_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"rank {r} ok" in o
+
+
+def test_bigvgan_state_dict_layouts_and_abi_order():
+    """BigVGAN drop-in: strict load of a folded checkpoint, weight-norm round trip, and the weight list handed to
+    the C ABI (state-dict order without the Activation1d filter buffers, then the 12 taps once)."""
+    from audiogpt_b200.vocoder.bigvgan.models import BigVGAN
+    h = specs.BIGVGAN_SMALL
+    sd = specs.synth_bigvgan(h, 4321)
+    m = BigVGAN(h)
+    assert any(k.endswith("weight_g") for k in m.state_dict())
+    m.load_state_dict(sd, strict=True)                   # folded checkpoint into a weight-normed module
+    assert set(m.state_dict()) == set(sd)
+    fw = m.folded_weights()
+    n_act = sum(1 for k in sd if k.endswith(".act.alpha"))
+    assert n_act == 4 * 3 * 6 + 1 and len(fw) == len(sd) - 2 * n_act + 1
+    assert fw[-1].shape == (12,) and abs(float(fw[-1].sum()) - 1.0) < 1e-6
+    assert torch.equal(fw[0], sd["conv_pre.weight"]) and torch.equal(fw[-3], sd["conv_post.weight"])
+    m2 = BigVGAN(h)                                       # g/v checkpoint -> folded module
+    sd_wn = m2.state_dict()
+    m3 = BigVGAN(h)
+    m3.remove_weight_norm()
+    m3.load_state_dict(sd_wn, strict=True)
+    for a, b in zip(m2.folded_weights(), m3.folded_weights()):
+        assert torch.allclose(a, b, atol=1e-7)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m(torch.zeros(1, 80, 4))
