@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-i", str(self.gpu), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-i", str(self.gpu), "-lms", "25"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
