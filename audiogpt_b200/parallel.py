@@ -111,3 +111,39 @@ def lpt_assign(costs: Sequence[float], workers: int) -> List[List[int]]:
         out[w].append(i)
         load[w] += costs[i]
     return out
+
+
+def run_mixed(jobs: Sequence[Tuple[str, int]], run_job, *, sync=None) -> Dict[str, object]:
+    """BASELINE configs[4] (mixed dispatch): ``jobs`` = [(kind, frames), ...] known to every rank in the same
+    order; greedy-LPT assignment by the FLOP cost model, every rank runs its own jobs with
+    ``run_job(index, kind, frames)`` (no data-path collective), then ONE all_gather of the per-rank timings.
+
+    Returns, on every rank: ``assignment`` (per-rank job indices), ``busy_s`` (per-rank busy seconds),
+    ``makespan_s`` (max over ranks), ``jobs_per_s`` and ``busy_fraction`` (busy / makespan per rank).
+    ``sync`` is called before each clock read (pass ``torch.cuda.synchronize`` on a GPU box)."""
+    import time
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    costs = [job_cost_tflop(k, f) for k, f in jobs]
+    assignment = lpt_assign(costs, world)
+    if sync:
+        sync()
+    t0 = time.perf_counter()
+    for i in assignment[rank]:
+        run_job(i, jobs[i][0], jobs[i][1])
+    if sync:
+        sync()
+    busy = time.perf_counter() - t0
+    if world > 1:
+        dev = (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu"))
+        mine = torch.tensor([busy], dtype=torch.float64, device=dev)
+        allb = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allb, mine)
+        busy_s = [float(v) for v in allb.cpu()]
+    else:
+        busy_s = [busy]
+    mk = max(busy_s)
+    return {"assignment": assignment, "busy_s": busy_s, "makespan_s": mk,
+            "jobs_per_s": len(jobs) / mk if mk > 0 else float("inf"),
+            "busy_fraction": [b / mk if mk > 0 else 1.0 for b in busy_s],
+            "model_load_tflop": [sum(costs[i] for i in w) for w in assignment]}

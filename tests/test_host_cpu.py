@@ -177,6 +177,15 @@ allw = parallel.all_gather_rows(mine, counts=[3, 2])
 assert allw.shape == (5, 1, 7) and torch.equal(allw[:, 0, 0], torch.arange(5.0))
 eq = parallel.all_gather_rows(torch.full((2, 3), float(rank)))
 assert eq.shape == (4, 3) and eq[0, 0] == 0 and eq[3, 0] == 1
+# mixed dispatch (BASELINE configs[4]): LPT assignment, every job exactly once, one all_gather of timings
+import time
+jobs = [("tts", 200 + 37 * i) for i in range(6)] + [("t2a", 0)] * 2
+done = []
+res = parallel.run_mixed(jobs, lambda i, kind, frames: (done.append(i), time.sleep(0.01 if kind == "tts" else 0.05)))
+assert sorted(res["assignment"][0] + res["assignment"][1]) == list(range(8))
+assert done == res["assignment"][rank] and len(res["busy_s"]) == 2
+assert res["makespan_s"] >= max(res["busy_s"]) - 1e-9 and abs(max(res["busy_fraction"]) - 1.0) < 1e-9
+assert abs(res["model_load_tflop"][0] - res["model_load_tflop"][1]) < 1.0     # one t2a clip (~19 TFLOP) on each rank
 print("rank", rank, "ok", flush=True)
 import torch.distributed as dist
 dist.barrier()
