@@ -9,6 +9,7 @@ static thread_local std::string g_last_error;
 static std::atomic<long long> g_launches{0};
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 void count_launch(long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count_now() { return g_launches.load(std::memory_order_relaxed); }
 
 template <typename F>
 static int guarded(F&& f) {
@@ -59,10 +60,13 @@ double agpt_fma_peak_tflops(void) {
 void agpt_destroy(agpt_handle h) {
   auto* p = reinterpret_cast<Handle*>(h);
   if (!p) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
   cudaSetDevice(p->device);
   cudaDeviceSynchronize();
   p->magic = 0;
   delete p;
+  if (prev >= 0) cudaSetDevice(prev);
 }
 
 int agpt_hifigan_create(const agpt_hifigan_cfg* cfg, const float* const* host_weights, int n_weights,
@@ -120,6 +124,21 @@ int agpt_gd_p_sample(agpt_handle h_or_null, const float* x, const float* eps_or_
   });
 }
 
+int agpt_gd_sample_loop(agpt_handle h, float* x_io, int t_hi, int t_lo, const float* coef_host, const float* noises_or_null,
+                        long noise_step_stride, int clip_denoised, void* stream) {
+  return guarded([&] {
+    AGPT_CHECK(x_io && coef_host, "null argument");
+    gd_sample_loop(as(h, kMagicDiffnet, "diffnet"), x_io, t_hi, t_lo, coef_host, noises_or_null, noise_step_stride,
+                   clip_denoised, (cudaStream_t)stream);
+  });
+}
+
+long agpt_diffnet_launches_per_step(agpt_handle h) {
+  long n = -1;
+  guarded([&] { n = diffnet_launches_per_step(as(h, kMagicDiffnet, "diffnet")); });
+  return n;
+}
+
 int agpt_axpby5(const float* x, const float* e0, const float* e1, const float* e2, const float* e3,
                 const float* coef_host, int B, long n_per_sample, float* out, void* stream) {
   return guarded([&] {
@@ -162,12 +181,18 @@ int agpt_ddim_update(const float* x, const float* eps2, int eps2_is_single, floa
 
 int agpt_unet_ddim_sample(agpt_handle h, const float* x_T, int B, int H, int W, int S, const int* t_steps_host,
                           const float* a_t, const float* a_prev, const float* sigma, const float* sqrt_om,
-                          float cfg_scale, float* x_out, void* stream) {
+                          float cfg_scale, float* x_out, float* pred_x0_or_null, void* stream) {
   return guarded([&] {
-    AGPT_CHECK(x_T && t_steps_host && a_t && a_prev && sigma && sqrt_om && x_out && S >= 1, "null argument");
+    AGPT_CHECK(x_T && t_steps_host && a_t && a_prev && sigma && sqrt_om && x_out && S >= 1 && B >= 1, "null argument");
     unet_ddim_sample(as(h, kMagicUnet, "unet"), x_T, B, H, W, S, t_steps_host, a_t, a_prev, sigma, sqrt_om, cfg_scale,
-                     x_out, (cudaStream_t)stream);
+                     x_out, pred_x0_or_null, (cudaStream_t)stream);
   });
+}
+
+long agpt_unet_launches_per_step(agpt_handle h) {
+  long n = -1;
+  guarded([&] { n = unet_launches_per_step(as(h, kMagicUnet, "unet")); });
+  return n;
 }
 
 int agpt_bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, int epi_res, int use_tc, int reps,

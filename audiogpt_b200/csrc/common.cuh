@@ -63,6 +63,21 @@ struct DevBuf {
   }
 };
 
+// RAII device scope for the C-ABI entry points: the reference deployment pins tools to different GPUs in ONE
+// process (audio-chatgpt.py:1051-1073), so an entry point must leave the calling thread's current device as it
+// found it (torch reads it back with cudaGetDevice).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    AGPT_CUDA(cudaGetDevice(&prev));
+    if (prev != dev) { AGPT_CUDA(cudaSetDevice(dev)); switched = true; }
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // Base of every opaque handle handed across the C ABI.
 struct Handle {
   uint32_t magic = 0;

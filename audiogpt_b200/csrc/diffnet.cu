@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "tapconv.cuh"
 #include "models.h"
+#include "nn_kernels.h"
 
 namespace agpt {
 
@@ -37,6 +38,37 @@ __global__ void p_sample_kernel(const float* __restrict__ x, const float* __rest
     float o = c1 * x0 + c2 * xv;
     if (noise) o += s * noise[base + i];
     out[base + i] = o;
+  }
+}
+
+// table versions for the graph-replayed loop: step k = *ctr handles t = t_hi - 1 - k
+__global__ void diff_step_embed_dev_kernel(float* __restrict__ out, const int* __restrict__ t, int C, float neg_emb) {
+  const int b = blockIdx.x;
+  const int half = C / 2;
+  const float tv = (float)t[b];
+  for (int j = threadIdx.x; j < C; j += blockDim.x) {
+    const int i = j < half ? j : j - half;
+    const float f = expf((float)i * neg_emb);
+    const float a = tv * f;
+    out[(long)b * C + j] = j < half ? sinf(a) : cosf(a);
+  }
+}
+__global__ void p_sample_tab_kernel(float* __restrict__ x, const float* __restrict__ eps, const float* const* __restrict__ noises_pp,
+                                    long noise_stride, const float* __restrict__ coef_tab, const int* __restrict__ ctr,
+                                    int nsteps, int clip, long n) {
+  const int k = *ctr;
+  const float* coef = coef_tab + 5 * (long)k;
+  const float A = coef[0], Bc = coef[1], c1 = coef[2], c2 = coef[3], s = coef[4];
+  const float* noises = *noises_pp;      // per-call base pointer lives in device memory: the captured step stays valid
+  const float* noise = noises ? noises + (long)(nsteps - 1 - k) * noise_stride : nullptr;
+  const long base = (long)blockIdx.y * n;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float xv = x[base + i];
+    float x0 = A * xv - Bc * eps[base + i];
+    if (clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+    float o = c1 * x0 + c2 * xv;
+    if (noise) o += s * noise[base + i];
+    x[base + i] = o;
   }
 }
 
@@ -87,6 +119,17 @@ struct Diffnet : Handle {
   // state
   int B = 0, T = 0;
   DevBuf condT, condp, xT, xcur, z, skip, hbuf, emb, e1, e2, dproj, eps_tmp;
+  // sampling-loop state (one captured step replayed; see gd_sample_loop)
+  DevBuf dproj_table, dproj_cur, coef_table, t_dev, step_ctr, loop_eps, loop_x;
+  cudaGraphExec_t step_graph = nullptr;
+  cudaStream_t cap_stream = nullptr;
+  struct GraphKey { int B = 0, T = 0, nsteps = 0, clip = 0; const void *x = nullptr, *condp = nullptr, *xcur = nullptr, *z = nullptr; long stride = 0; } gkey;
+  long launches_per_step = 0;
+
+  ~Diffnet() override {
+    if (step_graph) cudaGraphExecDestroy(step_graph);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+  }
 
   void set_cond(const float* cond, int B_, int T_, cudaStream_t st) {
     const int H = cfg.hidden_size, C = cfg.residual_channels, L = cfg.residual_layers;
@@ -102,30 +145,46 @@ struct Diffnet : Handle {
     tapconv_launch(P, st);
   }
 
-  void eps(const float* x, const int* t_host, float* out, cudaStream_t st) {
-    AGPT_CHECK(B > 0, "agpt_diffnet_set_cond must be called first");
+  void ensure_bufs() {
     const int C = cfg.residual_channels, L = cfg.residual_layers, M = cfg.in_dims;
     const size_t rows = (size_t)B * T;
     xT.ensure(rows * M); xcur.ensure(rows * C); z.ensure(rows * C); skip.ensure(rows * C); hbuf.ensure(rows * C);
     emb.ensure((size_t)B * C); e1.ensure((size_t)B * 4 * C); e2.ensure((size_t)B * C); dproj.ensure((size_t)B * L * C);
+  }
 
+  // diffusion-step embedding MLP and the per-layer diffusion projections for `rows` timestep embeddings
+  // (net.py:118-119, 67): embv [rows][C] -> out [rows][L*C]; e1v / e2v are scratch of rows*4C / rows*C floats
+  void step_mlp(const float* embv, int rows, float* e1v, float* e2v, float* out, cudaStream_t st) {
+    const int C = cfg.residual_channels, L = cfg.residual_layers;
+    auto lin = [&](const PackedConv& pc, const float* in, int cin, float* o, int cout, int epi) {
+      TapConvParams P = tapconv_params(pc, 1, rows, 0, 1);
+      P.in = in; P.in_gstride = 0; P.in_pitch = cin;
+      P.out = o; P.out_gstride = 0; P.out_pitch = cout;
+      P.epi = epi;
+      tapconv_launch(P, st);
+    };
+    lin(mlp0, embv, C, e1v, 4 * C, EPI_MISH);
+    lin(mlp2, e1v, 4 * C, e2v, C, EPI_BIAS);
+    lin(dproj_all, e2v, C, out, L * C, EPI_BIAS);
+  }
+
+  void eps(const float* x, const int* t_host, float* out, cudaStream_t st) {
+    AGPT_CHECK(B > 0, "agpt_diffnet_set_cond must be called first");
+    const int C = cfg.residual_channels, L = cfg.residual_layers;
+    ensure_bufs();
     StepT stp;
     for (int b = 0; b < B; ++b) stp.t[b] = t_host[b];
     const float neg_emb = (float)(-(std::log(10000.0) / (double)(C / 2 - 1)));
     diff_step_embed_kernel<<<B, 128, 0, st>>>(emb.p, stp, B, C, neg_emb);
     count_launch(1);
     AGPT_CUDA(cudaGetLastError());
-    auto lin = [&](const PackedConv& pc, const float* in, int cin, float* o, int cout, int epi) {
-      TapConvParams P = tapconv_params(pc, 1, B, 0, 1);
-      P.in = in; P.in_gstride = 0; P.in_pitch = cin;
-      P.out = o; P.out_gstride = 0; P.out_pitch = cout;
-      P.epi = epi;
-      tapconv_launch(P, st);
-    };
-    lin(mlp0, emb.p, C, e1.p, 4 * C, EPI_MISH);
-    lin(mlp2, e1.p, 4 * C, e2.p, C, EPI_BIAS);
-    lin(dproj_all, e2.p, C, dproj.p, L * C, EPI_BIAS);
+    step_mlp(emb.p, B, e1.p, e2.p, dproj.p, st);
+    eps_core(x, dproj.p, L * C, out, st);
+  }
 
+  // everything after the step embedding; dprojv [.][L*C] with per-sample row stride dproj_gs (0: shared row)
+  void eps_core(const float* x, const float* dprojv, int dproj_gs, float* out, cudaStream_t st) {
+    const int C = cfg.residual_channels, L = cfg.residual_layers, M = cfg.in_dims;
     launch_cf_to_cl(x, xT.p, B, M, T, st);
     {
       TapConvParams P = tapconv_params(in_proj, B, T, 0, 1);
@@ -140,7 +199,7 @@ struct Diffnet : Handle {
       {  // y = dilated_conv(x + dproj) + cond_proj ; z = sigmoid(gate)*tanh(filter)   (net.py:67-74)
         TapConvParams P = tapconv_params(dil[l], B, T, 0, d);
         P.in = xcur.p; P.in_gstride = gs; P.in_pitch = C;
-        P.pro = PRO_ADDVEC; P.pvec = dproj.p + (long)l * C; P.pvec_gstride = L * C;
+        P.pro = PRO_ADDVEC; P.pvec = dprojv + (long)l * C; P.pvec_gstride = dproj_gs;
         P.epi = EPI_GATE;
         P.res = condp.p + (long)l * 2 * C; P.res_gstride = (long)T * L * 2 * C; P.res_pitch = L * 2 * C;
         P.out = z.p; P.out_gstride = gs; P.out_pitch = C;
@@ -173,7 +232,7 @@ struct Diffnet : Handle {
 };
 
 Handle* diffnet_create(const agpt_diffnet_cfg* cfg, const float* const* W, int nW, int device) {
-  AGPT_CUDA(cudaSetDevice(device));
+  DeviceGuard dg_(device);
   auto* h = new Diffnet();
   h->magic = kMagicDiffnet; h->device = device; h->cfg = *cfg;
   const int C = cfg->residual_channels, H = cfg->hidden_size, M = cfg->in_dims, L = cfg->residual_layers;
@@ -207,22 +266,24 @@ Handle* diffnet_create(const agpt_diffnet_cfg* cfg, const float* const* W, int n
 
 void diffnet_set_cond(Handle* hh, const float* cond, int B, int T, cudaStream_t st) {
   auto* h = static_cast<Diffnet*>(hh);
-  AGPT_CUDA(cudaSetDevice(h->device));
+  DeviceGuard dg_(h->device);
   h->set_cond(cond, B, T, st);
 }
 
 void diffnet_eps(Handle* hh, const float* x, const int* t_host, float* eps, cudaStream_t st) {
   auto* h = static_cast<Diffnet*>(hh);
-  AGPT_CUDA(cudaSetDevice(h->device));
+  DeviceGuard dg_(h->device);
   h->eps(x, t_host, eps, st);
 }
 
 void gd_p_sample(Handle* hh, const float* x, const float* eps_or_null, const int* t_host, const float* coef_host,
                  const float* noise, int clip, int B, long n, float* x_out, cudaStream_t st) {
   const float* e = eps_or_null;
+  int dev_cur = 0;
+  AGPT_CUDA(cudaGetDevice(&dev_cur));
+  DeviceGuard dg_(e ? dev_cur : static_cast<Diffnet*>(hh)->device);
   if (!e) {
     auto* h = static_cast<Diffnet*>(hh);
-    AGPT_CUDA(cudaSetDevice(h->device));
     AGPT_CHECK(B == h->B && n == (long)h->cfg.in_dims * h->T, "shape differs from the cond set by agpt_diffnet_set_cond");
     h->eps_tmp.ensure((size_t)B * n);
     h->eps(x, t_host, h->eps_tmp.p, st);
@@ -234,5 +295,97 @@ void gd_p_sample(Handle* hh, const float* x, const float* eps_or_null, const int
   count_launch(1);
   AGPT_CUDA(cudaGetLastError());
 }
+
+// Whole ancestral sampling loop (shallow_diffusion_tts.py:263-272): for t = t_hi-1 .. t_lo: x <- p_sample(x, t, noise_t),
+// every sample at the same t (as the reference's loop does).  The step-embedding MLP and the 20 diffusion
+// projections run ONCE for all steps (one GEMM of nsteps rows); step 0 runs eagerly, then ONE captured step
+// (CUDA graph; device step counter, coefficient / projection tables) is replayed.  coef_host [nsteps][5] rows in
+// sampling order (row k belongs to t = t_hi-1-k); noises: device [nsteps][B][n] indexed by t - t_lo, or NULL.
+void gd_sample_loop(Handle* hh, float* x_io, int t_hi, int t_lo, const float* coef_host, const float* noises,
+                    long noise_stride, int clip, cudaStream_t st) {
+  auto* h = static_cast<Diffnet*>(hh);
+  DeviceGuard dg_(h->device);
+  AGPT_CHECK(h->B > 0, "agpt_diffnet_set_cond must be called first");
+  const int nsteps = t_hi - t_lo;
+  AGPT_CHECK(nsteps >= 1 && t_lo >= 0, "empty step range");
+  const int C = h->cfg.residual_channels, L = h->cfg.residual_layers, M = h->cfg.in_dims, B = h->B;
+  const long n = (long)M * h->T;
+  h->ensure_bufs();
+  h->dproj_table.ensure((size_t)nsteps * L * C);
+  h->dproj_cur.ensure((size_t)L * C);
+  h->coef_table.ensure((size_t)nsteps * 5);
+  h->t_dev.ensure((size_t)nsteps);
+  h->step_ctr.ensure(4);
+  h->loop_eps.ensure((size_t)B * n);
+  h->loop_x.ensure((size_t)B * n);
+  std::vector<int> ts(nsteps);
+  for (int k = 0; k < nsteps; ++k) ts[k] = t_hi - 1 - k;
+  AGPT_CUDA(cudaMemcpyAsync(h->t_dev.p, ts.data(), (size_t)nsteps * sizeof(int), cudaMemcpyHostToDevice, st));
+  AGPT_CUDA(cudaMemcpyAsync(h->coef_table.p, coef_host, (size_t)nsteps * 5 * sizeof(float), cudaMemcpyHostToDevice, st));
+  AGPT_CUDA(cudaMemsetAsync(h->step_ctr.p, 0, sizeof(int), st));
+  AGPT_CUDA(cudaMemcpyAsync(h->step_ctr.p + 2, &noises, sizeof(noises), cudaMemcpyHostToDevice, st));   // floats 2..3 = the pointer slot
+  AGPT_CUDA(cudaMemcpyAsync(h->loop_x.p, x_io, (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  AGPT_CUDA(cudaStreamSynchronize(st));        // ts / coef_host / &noises are host memory
+  {
+    DevBuf &te = h->z, &t1 = h->skip, &t2 = h->hbuf;      // scratch: free before the first step
+    te.ensure((size_t)nsteps * C); t1.ensure((size_t)nsteps * 4 * C); t2.ensure((size_t)nsteps * C);
+    const float neg_emb = (float)(-(std::log(10000.0) / (double)(C / 2 - 1)));
+    diff_step_embed_dev_kernel<<<nsteps, 128, 0, st>>>(te.p, reinterpret_cast<const int*>(h->t_dev.p), C, neg_emb);
+    count_launch(1);
+    AGPT_CUDA(cudaGetLastError());
+    h->step_mlp(te.p, nsteps, t1.p, t2.p, h->dproj_table.p, st);
+    h->ensure_bufs();                                        // (scratch may have grown the buffers: keep sizes valid)
+  }
+  int* ctr = reinterpret_cast<int*>(h->step_ctr.p);
+  const float* const* noise_pp = reinterpret_cast<const float* const*>(h->step_ctr.p + 2);
+  float* xl = h->loop_x.p;
+  auto step = [&](cudaStream_t s) {
+    select_row(h->dproj_table.p, ctr, h->dproj_cur.p, L * C, s);
+    h->eps_core(xl, h->dproj_cur.p, 0, h->loop_eps.p, s);
+    dim3 grid((unsigned)std::min<long>(cdivl(n, 256), 1184), B);
+    p_sample_tab_kernel<<<grid, 256, 0, s>>>(xl, h->loop_eps.p, noise_pp, noise_stride, h->coef_table.p, ctr, nsteps, clip, n);
+    count_launch(1);
+    AGPT_CUDA(cudaGetLastError());
+    step_inc(ctr, s);
+  };
+  static int allow_graph = -1;
+  if (allow_graph < 0) { const char* e = getenv("AGPT_GRAPH"); allow_graph = (e && e[0] == '0') ? 0 : 1; }
+  const long long l0 = launch_count_now();
+  step(st);
+  h->launches_per_step = (long)(launch_count_now() - l0);
+  int done = 1;
+  if (allow_graph && nsteps > 1 && !profile_enabled()) {
+    Diffnet::GraphKey k;
+    k.B = B; k.T = h->T; k.nsteps = nsteps; k.clip = clip; k.x = xl; k.condp = h->condp.p; k.xcur = h->xcur.p; k.z = h->z.p; k.stride = noise_stride;
+    const Diffnet::GraphKey& o = h->gkey;
+    const bool same = h->step_graph && k.B == o.B && k.T == o.T && k.nsteps == o.nsteps && k.clip == o.clip && k.x == o.x &&
+                      k.condp == o.condp && k.xcur == o.xcur && k.z == o.z && k.stride == o.stride;
+    if (!same) {
+      if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; }
+      cudaGraph_t g = nullptr;
+      if (!h->cap_stream) AGPT_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+      AGPT_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        step(h->cap_stream);
+      } catch (...) {
+        cudaStreamEndCapture(h->cap_stream, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+      }
+      AGPT_CUDA(cudaStreamEndCapture(h->cap_stream, &g));
+      const cudaError_t ie = cudaGraphInstantiate(&h->step_graph, g, 0);
+      cudaGraphDestroy(g);
+      AGPT_CUDA(ie);
+      h->gkey = k;
+      count_launch(-h->launches_per_step);
+    }
+    for (; done < nsteps; ++done) AGPT_CUDA(cudaGraphLaunch(h->step_graph, st));
+    count_launch(h->launches_per_step * (nsteps - 1));
+  }
+  for (; done < nsteps; ++done) step(st);
+  AGPT_CUDA(cudaMemcpyAsync(x_io, xl, (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+}
+
+long diffnet_launches_per_step(Handle* hh) { return static_cast<Diffnet*>(hh)->launches_per_step; }
 
 }  // namespace agpt

@@ -325,7 +325,7 @@ struct Hifigan : Handle {
 };
 
 Handle* hifigan_create(const agpt_hifigan_cfg* cfg, const float* const* W, int nW, int device) {
-  AGPT_CUDA(cudaSetDevice(device));
+  DeviceGuard dg_(device);
   auto* h = new Hifigan();
   h->magic = kMagicHifigan; h->device = device; h->cfg = *cfg;
   const int nu = cfg->num_upsamples, nk = cfg->num_kernels;
@@ -441,13 +441,13 @@ static void hifigan_forward_l2(Hifigan* h, const float* mel, const float* har, i
 
 void hifigan_forward(Handle* hh, const float* mel, const float* har, int B, int T, float* wav, cudaStream_t st) {
   auto* h = static_cast<Hifigan*>(hh);
-  AGPT_CUDA(cudaSetDevice(h->device));
+  DeviceGuard dg_(h->device);
   hifigan_forward_l2(h, mel, har, B, T, wav, st);
 }
 
 void hifigan_vocode_host(Handle* hh, const float* mel_host, const float* har_host, int B, int T, float* wav_host) {
   auto* h = static_cast<Hifigan*>(hh);
-  AGPT_CUDA(cudaSetDevice(h->device));
+  DeviceGuard dg_(h->device);
   if (!h->own_stream) AGPT_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   const size_t nmel = (size_t)B * h->cfg.n_mels * T, nwav = (size_t)B * h->cfg.c_out * T * h->hop;
   const size_t nhar = (size_t)B * T * h->hop;

@@ -6,6 +6,8 @@
 namespace agpt {
 
 void count_launch(long n);
+long long launch_count_now();
+bool profile_enabled();
 
 void launch_cf_to_cl(const float* in, float* out, int B, int C, int T, cudaStream_t st);
 
@@ -18,6 +20,9 @@ void diffnet_set_cond(Handle* h, const float* cond, int B, int T, cudaStream_t s
 void diffnet_eps(Handle* h, const float* x, const int* t_host, float* eps, cudaStream_t st);
 void gd_p_sample(Handle* h_or_null, const float* x, const float* eps_or_null, const int* t_host, const float* coef_host,
                  const float* noise, int clip, int B, long n, float* x_out, cudaStream_t st);
+void gd_sample_loop(Handle* h, float* x_io, int t_hi, int t_lo, const float* coef_host, const float* noises,
+                    long noise_stride, int clip, cudaStream_t st);
+long diffnet_launches_per_step(Handle* h);
 void axpby5(const float* x, const float* e0, const float* e1, const float* e2, const float* e3,
             const float* coef_host, int B, long n, float* out, cudaStream_t st);
 
@@ -26,7 +31,8 @@ void unet_set_context(Handle* h, const float* ctx, int N, int S, cudaStream_t st
 void unet_forward(Handle* h, const float* x, const int* t_host, int N, int H, int W, float* eps, cudaStream_t st);
 void unet_ddim_sample(Handle* h, const float* x_T, int B, int H, int W, int S, const int* t_steps,
                       const float* a_t, const float* a_prev, const float* sigma, const float* sqrt_om,
-                      float cfg_scale, float* x_out, cudaStream_t st);
+                      float cfg_scale, float* x_out, float* pred_x0_out, cudaStream_t st);
+long unet_launches_per_step(Handle* h);
 
 void bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, int epi_res, int use_tc, int reps,
                    int check, double* out, double* dbg_avg);

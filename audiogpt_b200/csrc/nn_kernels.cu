@@ -10,90 +10,105 @@
 namespace agpt {
 
 // ------------------------------------------------------------------ GroupNorm
-// pass 1: per (n, row-split, group) partial sum / sum of squares, accumulated in double
-// (per-thread channel sums -> shared-memory per-group reduction); grid (S, N)
-constexpr int GN_MAX_SPLIT = 32;
-__global__ void gn_partial_kernel(const float* __restrict__ x, double* __restrict__ part, int HW, int C, int S, int G) {
-  __shared__ double sg[64][2];
-  const int n = blockIdx.y, s = blockIdx.x;
-  const int r0 = (int)((long)HW * s / S), r1 = (int)((long)HW * (s + 1) / S);
-  const int cpg = C / G;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) { sg[g][0] = 0.0; sg[g][1] = 0.0; }
+// One CTA per (sample, group): the group's slab -- HW rows x cpg contiguous channels -- is read ONCE into shared
+// memory (when it fits: every UNet shape does; the VAE's 80x624 maps fall back to re-reading through L2), then
+// mean, centred variance (exact two-pass, fp32 per thread / double across threads) and the normalised
+// (+SiLU) output come from the cached copy.  Replaces round 1's gn_partial + gn_apply pair (fp64 shared
+// atomics, a serial S x G fold per CTA: 57 us per call on the 8 MB UNet tensors).
+// Reference: GroupNorm32 / Normalize, ldm/modules/diffusionmodules/util.py:199-216, attention.py:76-77.
+constexpr int GN_THREADS = 512;
+constexpr int GN_CACHE_FLOATS = 48 * 1024;   // 192 KB of dynamic shared memory
+
+__device__ __forceinline__ double gn_block_sum(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   __syncthreads();
-  const float* xb = x + (long)n * HW * C;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    double a = 0.0, b = 0.0;
-    for (int r = r0; r < r1; ++r) {
-      const double v = (double)__ldg(xb + (long)r * C + c);
-      a += v; b += v * v;
-    }
-    atomicAdd(&sg[c / cpg][0], a);
-    atomicAdd(&sg[c / cpg][1], b);
-  }
+  if (l == 0) red[w] = v;
   __syncthreads();
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    double* o = part + (((long)n * S + s) * G + g) * 2;
-    o[0] = sg[g][0]; o[1] = sg[g][1];
-  }
+  double t = 0.0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+  return t;
 }
 
-// pass 2: every CTA folds the S x G partials of its sample (tiny) and normalises a slab of rows,
-// 128-bit loads/stores along the channel axis
-__global__ void gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ part,
-                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                float* __restrict__ y, int HW, int C, int S, int G, float eps, int silu, int rows_per_cta) {
-  __shared__ float mean[64], rstd[64];
-  const int n = blockIdx.y;
-  const int cpg = C / G;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    double a = 0.0, b = 0.0;
-    for (int s = 0; s < S; ++s) {
-      const double* p = part + (((long)n * S + s) * G + g) * 2;
-      a += p[0]; b += p[1];
-    }
-    const double cnt = (double)HW * cpg;
-    const double m = a / cnt;
-    double var = b / cnt - m * m;
-    if (var < 0.0) var = 0.0;
-    mean[g] = (float)m;
-    rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+template <int V>   // V = vector width in floats along the channel axis (cpg % V == 0)
+__global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               int HW, int C, int cpg, float eps, int silu, int cached) {
+  extern __shared__ __align__(16) float gn_cache[];
+  __shared__ double red[GN_THREADS / 32];
+  const int n = blockIdx.y, g = blockIdx.x;
+  const float* xb = x + (long)n * HW * C + g * cpg;
+  float* yb = y + (long)n * HW * C + g * cpg;
+  const int vpr = cpg / V;                 // vectors per row
+  const int nvec = HW * vpr;
+  // pass 1: sum (and fill the cache)
+  float s = 0.f;
+  for (int i = threadIdx.x; i < nvec; i += GN_THREADS) {
+    const int r = i / vpr, c = (i - r * vpr) * V;
+    float v[V];
+    if constexpr (V == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(xb + (long)r * C + c)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else if constexpr (V == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(xb + (long)r * C + c)); v[0] = t.x; v[1] = t.y; }
+    else v[0] = __ldg(xb + (long)r * C + c);
+#pragma unroll
+    for (int k = 0; k < V; ++k) { s += v[k]; if (cached) gn_cache[k * nvec + i] = v[k]; }
   }
-  __syncthreads();
-  const int r0 = blockIdx.x * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
-  const float* xb = x + (long)n * HW * C;
-  float* yb = y + (long)n * HW * C;
-  const int c4n = C >> 2;
-  const int total = (r1 - r0) * c4n;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int r = r0 + i / c4n, c = (i % c4n) << 2;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (long)r * C + c));
-    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
-    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
-    const int g0 = c / cpg, g1 = (c + 1) / cpg, g2 = (c + 2) / cpg, g3 = (c + 3) / cpg;
-    float4 o;
-    o.x = (v.x - mean[g0]) * rstd[g0] * ga.x + be.x;
-    o.y = (v.y - mean[g1]) * rstd[g1] * ga.y + be.y;
-    o.z = (v.z - mean[g2]) * rstd[g2] * ga.z + be.z;
-    o.w = (v.w - mean[g3]) * rstd[g3] * ga.w + be.w;
-    if (silu) { o.x = siluf_(o.x); o.y = siluf_(o.y); o.z = siluf_(o.z); o.w = siluf_(o.w); }
-    *reinterpret_cast<float4*>(yb + (long)r * C + c) = o;
+  const double cnt = (double)HW * cpg;
+  const float mean = (float)(gn_block_sum((double)s, red) / cnt);
+  // pass 2: centred sum of squares
+  float q = 0.f;
+  for (int i = threadIdx.x; i < nvec; i += GN_THREADS) {
+    const int r = i / vpr, c = (i - r * vpr) * V;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float d = (cached ? gn_cache[k * nvec + i] : __ldg(xb + (long)r * C + c + k)) - mean;
+      q = fmaf(d, d, q);
+    }
+  }
+  const float rstd = (float)(1.0 / sqrt(gn_block_sum((double)q, red) / cnt + (double)eps));
+  // pass 3: normalise (+ SiLU)
+  for (int i = threadIdx.x; i < nvec; i += GN_THREADS) {
+    const int r = i / vpr, c = (i - r * vpr) * V;
+    float o[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float xv = cached ? gn_cache[k * nvec + i] : __ldg(xb + (long)r * C + c + k);
+      float t = (xv - mean) * rstd * __ldg(gamma + g * cpg + c + k) + __ldg(beta + g * cpg + c + k);
+      if (silu) t = siluf_(t);
+      o[k] = t;
+    }
+    if constexpr (V == 4) *reinterpret_cast<float4*>(yb + (long)r * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+    else if constexpr (V == 2) *reinterpret_cast<float2*>(yb + (long)r * C + c) = make_float2(o[0], o[1]);
+    else yb[(long)r * C + c] = o[0];
   }
 }
 
 void groupnorm(const float* x, float* y, const float* gamma, const float* beta, int N, int HW, int C, int G,
                float eps, bool silu, double* scratch, cudaStream_t st) {
-  AGPT_CHECK(C % G == 0 && G <= 64 && C % 4 == 0, "GroupNorm: channels must be divisible by groups (<= 64) and by 4");
-  const int S = std::max(1, std::min(GN_MAX_SPLIT, HW / 8));
-  gn_partial_kernel<<<dim3(S, N), 256, 0, st>>>(x, scratch, HW, C, S, G);
-  // ~2 waves of CTAs over 148 SMs
-  const int target_ctas = std::max(1, 296 / N);
-  const int rows_per_cta = std::max(1, cdiv(HW, target_ctas));
-  gn_apply_kernel<<<dim3(cdiv(HW, rows_per_cta), N), 256, 0, st>>>(
-      x, scratch, gamma, beta, y, HW, C, S, G, eps, silu ? 1 : 0, rows_per_cta);
-  count_launch(2);
+  (void)scratch;
+  AGPT_CHECK(C % G == 0 && C % 4 == 0, "GroupNorm: channels must be divisible by the group count and by 4");
+  const int cpg = C / G;
+  const long slab = (long)HW * cpg;
+  const int cached = slab <= GN_CACHE_FLOATS ? 1 : 0;
+  const size_t smem = cached ? (size_t)slab * sizeof(float) : 0;
+  int dev = 0;
+  AGPT_CUDA(cudaGetDevice(&dev));
+  static bool attr_done_dev[64] = {false};
+  if (!attr_done_dev[dev & 63]) {
+    AGPT_CUDA(cudaFuncSetAttribute(gn_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GN_CACHE_FLOATS * 4));
+    AGPT_CUDA(cudaFuncSetAttribute(gn_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GN_CACHE_FLOATS * 4));
+    AGPT_CUDA(cudaFuncSetAttribute(gn_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GN_CACHE_FLOATS * 4));
+    attr_done_dev[dev & 63] = true;
+  }
+  const dim3 grid(G, N);
+  const int si = silu ? 1 : 0;
+  if (cpg % 4 == 0) gn_fused_kernel<4><<<grid, GN_THREADS, smem, st>>>(x, y, gamma, beta, HW, C, cpg, eps, si, cached);
+  else if (cpg % 2 == 0) gn_fused_kernel<2><<<grid, GN_THREADS, smem, st>>>(x, y, gamma, beta, HW, C, cpg, eps, si, cached);
+  else gn_fused_kernel<1><<<grid, GN_THREADS, smem, st>>>(x, y, gamma, beta, HW, C, cpg, eps, si, cached);
+  count_launch(1);
   AGPT_CUDA(cudaGetLastError());
 }
-size_t groupnorm_scratch_doubles(int N, int C) { (void)C; return (size_t)N * GN_MAX_SPLIT * 64 * 2; }
+size_t groupnorm_scratch_doubles(int N, int C) { (void)N; (void)C; return 16; }
 
 // ------------------------------------------------------------------ LayerNorm (one warp per row)
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
@@ -252,6 +267,46 @@ void timestep_embedding(float* out, const int* t_host, int N, int dim, cudaStrea
   AGPT_CUDA(cudaGetLastError());
 }
 
+// same, timesteps read from a device array (one row per DDIM step: the whole table is embedded once per sample() call)
+__global__ void timestep_embed_dev_kernel(float* __restrict__ out, const int* __restrict__ t, int dim) {
+  const int n = blockIdx.x, half = dim / 2;
+  const float tv = (float)t[n];
+  for (int j = threadIdx.x; j < dim; j += blockDim.x) {
+    float v = 0.f;
+    if (j < 2 * half) {
+      const int i = j < half ? j : j - half;
+      const float f = expf(-9.210340371976184f * (float)i / (float)half);
+      const float a = tv * f;
+      v = j < half ? cosf(a) : sinf(a);
+    }
+    out[(long)n * dim + j] = v;
+  }
+}
+void timestep_embedding_dev(float* out, const int* t_dev, int rows, int dim, cudaStream_t st) {
+  timestep_embed_dev_kernel<<<rows, 128, 0, st>>>(out, t_dev, dim);
+  count_launch(1);
+  AGPT_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ device-side step counter (CUDA-graph replays)
+// A denoising loop replays ONE captured step; everything that changes from step to step is read from device
+// tables indexed by a device counter: out[c] = table[*step][c]; the counter is bumped by the last node of the step.
+__global__ void select_row_kernel(const float* __restrict__ table, const int* __restrict__ step, float* __restrict__ out, int ncols) {
+  const long k = *step;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += gridDim.x * blockDim.x) out[c] = table[k * ncols + c];
+}
+void select_row(const float* table, const int* step_dev, float* out, int ncols, cudaStream_t st) {
+  select_row_kernel<<<std::min(64, cdiv(ncols, 256)), 256, 0, st>>>(table, step_dev, out, ncols);
+  count_launch(1);
+  AGPT_CUDA(cudaGetLastError());
+}
+__global__ void step_inc_kernel(int* step) { *step += 1; }
+void step_inc(int* step_dev, cudaStream_t st) {
+  step_inc_kernel<<<1, 1, 0, st>>>(step_dev);
+  count_launch(1);
+  AGPT_CUDA(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------ gathers
 __global__ void concat_kernel(const float* __restrict__ a, int Ca, const float* __restrict__ b, int Cb,
                               float* __restrict__ out, long rows) {
@@ -318,17 +373,19 @@ void im2col_stride2(const float* in, float* col, int N, int H, int W, int C, int
 }
 
 // [N][C][HW] -> [N][HW][Cpad] with zero fill for c >= C (tiny C, e.g. 4 latent channels)
-__global__ void cf_to_cl_pad_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int Cpad, int HW, long total) {
+// sample n reads source sample n % Nsrc: the doubled batch of classifier-free guidance (x_in = cat([x] * 2),
+// ddim.py:178) is produced here instead of by two device-to-device copies
+__global__ void cf_to_cl_pad_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int Cpad, int HW, long total, int Nsrc) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int c = (int)(i % Cpad);
     const long r = i / Cpad;
-    const long n = r / HW, p = r % HW;
+    const long n = (r / HW) % Nsrc, p = r % HW;
     out[i] = c < C ? in[(n * C + c) * HW + p] : 0.f;
   }
 }
-void cf_to_cl_pad(const float* in, float* out, int N, int C, int Cpad, int HW, cudaStream_t st) {
+void cf_to_cl_pad(const float* in, float* out, int N, int C, int Cpad, int HW, cudaStream_t st, int Nsrc) {
   const long total = (long)N * HW * Cpad;
-  cf_to_cl_pad_kernel<<<(unsigned)std::min<long>(cdivl(total, 256), 4096), 256, 0, st>>>(in, out, C, Cpad, HW, total);
+  cf_to_cl_pad_kernel<<<(unsigned)std::min<long>(cdivl(total, 256), 4096), 256, 0, st>>>(in, out, C, Cpad, HW, total, Nsrc > 0 ? Nsrc : N);
   count_launch(1);
   AGPT_CUDA(cudaGetLastError());
 }
@@ -350,6 +407,32 @@ __global__ void ddim_update_kernel(const float* __restrict__ x, const float* __r
     if (pred_x0) pred_x0[i] = p0;
   }
 }
+// Table version for graph replays: coef[*step] = {sqrt_at, sqrt_aprev, dir_coef, sigma_t, sqrt_om, cfg_scale};
+// x is updated in place (x_prev may alias x: every element is read before it is written by the same thread).
+__global__ void ddim_update_tab_kernel(const float* __restrict__ x, const float* __restrict__ eps2, int single,
+                                       const float* __restrict__ coef, const int* __restrict__ step, long total,
+                                       float* __restrict__ x_prev, float* __restrict__ pred_x0) {
+  const float* c = coef + 6 * (long)(*step);
+  const float sqrt_at = c[0], sqrt_aprev = c[1], dir_coef = c[2], sqrt_om = c[4], s = c[5];
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    float e;
+    if (single) e = eps2[i];
+    else { const float eu = eps2[i], ec = eps2[total + i]; e = eu + s * (ec - eu); }
+    const float xv = x[i];
+    const float p0 = (xv - sqrt_om * e) / sqrt_at;
+    x_prev[i] = sqrt_aprev * p0 + dir_coef * e + 0.f;
+    if (pred_x0) pred_x0[i] = p0;
+  }
+}
+void ddim_update_tab(const float* x, const float* eps2, int single, const float* coef_dev, const int* step_dev, int B, long n,
+                     float* x_prev, float* pred_x0, cudaStream_t st) {
+  const long total = (long)B * n;
+  ddim_update_tab_kernel<<<(unsigned)std::min<long>(cdivl(total, 256), 2048), 256, 0, st>>>(x, eps2, single, coef_dev, step_dev,
+                                                                                         total, x_prev, pred_x0);
+  count_launch(1);
+  AGPT_CUDA(cudaGetLastError());
+}
+
 void ddim_update(const float* x, const float* eps2, int single, float cfg_scale, float a_t, float a_prev,
                  float sigma_t, float sqrt_om, const float* noise, float temperature, int B, long n,
                  float* x_prev, float* pred_x0, cudaStream_t st) {

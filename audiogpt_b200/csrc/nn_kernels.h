@@ -15,7 +15,12 @@ void timestep_embedding(float* out, const int* t_host, int N, int dim, cudaStrea
 void concat_channels(const float* a, int Ca, const float* b, int Cb, float* out, long rows, cudaStream_t st);
 void upsample_nearest2(const float* in, float* out, int N, int H, int W, int C, cudaStream_t st);
 void im2col_stride2(const float* in, float* col, int N, int H, int W, int C, int Ho, int Wo, cudaStream_t st);
-void cf_to_cl_pad(const float* in, float* out, int N, int C, int Cpad, int HW, cudaStream_t st);
+void cf_to_cl_pad(const float* in, float* out, int N, int C, int Cpad, int HW, cudaStream_t st, int Nsrc = 0);
+void timestep_embedding_dev(float* out, const int* t_dev, int rows, int dim, cudaStream_t st);
+void select_row(const float* table, const int* step_dev, float* out, int ncols, cudaStream_t st);
+void step_inc(int* step_dev, cudaStream_t st);
+void ddim_update_tab(const float* x, const float* eps2, int single, const float* coef_dev, const int* step_dev, int B, long n,
+                     float* x_prev, float* pred_x0, cudaStream_t st);
 void ddim_update(const float* x, const float* eps2, int single, float cfg_scale, float a_t, float a_prev,
                  float sigma_t, float sqrt_om, const float* noise, float temperature, int B, long n,
                  float* x_prev, float* pred_x0, cudaStream_t st);

@@ -10,6 +10,8 @@ struct ProfRec { cudaEvent_t e0, e1; int variant; double flops, bytes; int G, L,
 static bool g_prof = false;
 static std::vector<ProfRec> g_recs;
 
+bool profile_enabled() { return g_prof; }
+
 void profile_enable(int on) {
   g_prof = on != 0;
   if (!on) {

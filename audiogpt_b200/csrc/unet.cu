@@ -58,7 +58,19 @@ struct Unet : Handle {
   DevBuf arena;
   size_t arena_off = 0, arena_cap = 0;
   DevBuf gn_scratch_f;  // doubles stored in a float buffer (2 floats per double)
-  DevBuf ddim_eps, ddim_x, ddim_x2;
+  DevBuf ddim_eps, ddim_x, ddim_p0;
+  // denoising-loop state: per-step tables on the device, a device step counter, one captured step (CUDA graph)
+  DevBuf emb_table, emb_cur, coef_table, tsteps_dev, step_ctr;
+  int emb_gstride = 0;            // row stride of the per-sample ResBlock embedding vectors (0: all samples share one row)
+  cudaGraphExec_t step_graph = nullptr;
+  cudaStream_t cap_stream = nullptr;
+  struct GraphKey { int N = 0, H = 0, W = 0, single = 0; const void *arena = nullptr, *ctx = nullptr, *x = nullptr; int ctxS = 0; } gkey;
+  long launches_per_step = 0;
+
+  ~Unet() override {
+    if (step_graph) cudaGraphExecDestroy(step_graph);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+  }
 
   float* alloc(size_t n) {
     n = (n + 63) & ~(size_t)63;
@@ -105,7 +117,7 @@ struct Unet : Handle {
     float* h1 = alloc((size_t)N * HW * r.cin);
     groupnorm(x, h1, r.gn1_g.p, r.gn1_b.p, N, HW, r.cin, 32, 1e-5f, true, scr, s);
     float* h2 = alloc((size_t)N * HW * r.cout);
-    conv3x3(r.conv1, h1, h2, N, H, W, EPI_ADDVEC, nullptr, emb_out + r.emb_off, emb_total, s);
+    conv3x3(r.conv1, h1, h2, N, H, W, EPI_ADDVEC, nullptr, emb_out + r.emb_off, emb_gstride, s);
     float* h3 = alloc((size_t)N * HW * r.cout);
     groupnorm(h2, h3, r.gn2_g.p, r.gn2_b.p, N, HW, r.cout, 32, 1e-5f, true, scr, s);
     const float* sk = x;
@@ -213,25 +225,27 @@ struct Unet : Handle {
     return (size_t)N * (nblocks * (2 * per_res + per_st + 3 * hw * maxc * 3)) + (1 << 20);
   }
 
-  void forward(const float* x, const int* t_host, int N, int H, int W, float* eps, cudaStream_t s) {
+  // time-embedding MLP + all ResBlock emb projections as ONE GEMM over `rows` timesteps (openaimodel.py:725-726,264):
+  // te [rows][mc] -> out [rows][emb_total].  Scratch comes from the arena (call before the blocks).
+  void embed_rows(const float* te, int rows, float* out, cudaStream_t s) {
+    float* e1 = alloc((size_t)rows * temb);
+    linear(time0, te, mc, e1, temb, rows, EPI_SILU, nullptr, 0, s);
+    float* emb = alloc((size_t)rows * temb);
+    linear(time2, e1, temb, emb, temb, rows, EPI_BIAS, nullptr, 0, s);
+    linear(emb_all, emb, temb, out, emb_total, rows, EPI_BIAS, nullptr, 0, s, PRO_SILU);
+  }
+
+  void prepare(int N, int H, int W) {
     AGPT_CHECK(N >= 1 && N <= 256 && H >= 1 && W >= 1, "bad UNet input shape");
     const size_t need = arena_need(N, H, W);
     if (need > arena_cap) { arena.ensure(need); arena_cap = need; }
-    arena_off = 0;
-    gn_scratch_f.ensure(groupnorm_scratch_doubles(N, 4 * temb) * 2);
+    gn_scratch_f.ensure(64);
+  }
 
-    // time embedding MLP + all ResBlock emb projections in one GEMM   (openaimodel.py:725-726,264)
-    float* te = alloc((size_t)N * mc);
-    timestep_embedding(te, t_host, N, mc, s);
-    float* e1 = alloc((size_t)N * temb);
-    linear(time0, te, mc, e1, temb, N, EPI_SILU, nullptr, 0, s);
-    float* emb = alloc((size_t)N * temb);
-    linear(time2, e1, temb, emb, temb, N, EPI_BIAS, nullptr, 0, s);
-    float* emb_out = alloc((size_t)N * emb_total);
-    linear(emb_all, emb, temb, emb_out, emb_total, N, EPI_BIAS, nullptr, 0, s, PRO_SILU);
-
+  // everything after the embedding: x [Nsrc][C][H][W] (sample n reads n % Nsrc) -> eps [N][Cout][H][W]
+  void forward_core(const float* x, int Nsrc, const float* emb_out, int N, int H, int W, float* eps, cudaStream_t s) {
     float* x_cl = alloc((size_t)N * H * W * cin_pad);
-    cf_to_cl_pad(x, x_cl, N, cfg.in_channels, cin_pad, H * W, s);
+    cf_to_cl_pad(x, x_cl, N, cfg.in_channels, cin_pad, H * W, s, Nsrc);
     Act a{x_cl, cin_pad, H, W};
     std::vector<Act> hs;
     for (const Block& b : in_blocks) { a = run_block(b, a, emb_out, N, s); hs.push_back(a); }
@@ -253,12 +267,35 @@ struct Unet : Handle {
       tapconv_launch(P, s);
     }
   }
+
+  void forward(const float* x, const int* t_host, int N, int H, int W, float* eps, cudaStream_t s) {
+    prepare(N, H, W);
+    arena_off = 0;
+    float* te = alloc((size_t)N * mc);
+    timestep_embedding(te, t_host, N, mc, s);
+    float* emb_out = alloc((size_t)N * emb_total);
+    embed_rows(te, N, emb_out, s);
+    emb_gstride = emb_total;
+    forward_core(x, N, emb_out, N, H, W, eps, s);
+  }
+
+  // One DDIM step of the on-device loop: everything step-dependent comes from device tables indexed by step_ctr,
+  // so the launch sequence is identical for every step (capturable once, replayed S - 1 times).
+  void ddim_step(int B, int N, int H, int W, long n, cudaStream_t s) {
+    arena_off = 0;
+    int* ctr = reinterpret_cast<int*>(step_ctr.p);
+    select_row(emb_table.p, ctr, emb_cur.p, emb_total, s);
+    emb_gstride = 0;
+    forward_core(ddim_x.p, B, emb_cur.p, N, H, W, ddim_eps.p, s);
+    ddim_update_tab(ddim_x.p, ddim_eps.p, N == B ? 1 : 0, coef_table.p, ctr, B, n, ddim_x.p, ddim_p0.p, s);
+    step_inc(ctr, s);
+  }
 };
 
 static void upload_vec(DevBuf& d, const float* p, int n) { d.upload(std::vector<float>(p, p + n)); }
 
 Handle* unet_create(const agpt_unet_cfg* cfg, const float* const* W, int nW, int device) {
-  AGPT_CUDA(cudaSetDevice(device));
+  DeviceGuard dg_(device);
   auto* u = new Unet();
   u->magic = kMagicUnet; u->device = device; u->cfg = *cfg;
   const int mc = cfg->model_channels, temb = 4 * mc, ctx = cfg->context_dim, depth = cfg->transformer_depth;
@@ -407,43 +444,100 @@ Handle* unet_create(const agpt_unet_cfg* cfg, const float* const* W, int nW, int
 
 void unet_set_context(Handle* hh, const float* ctx, int N, int S, cudaStream_t st) {
   auto* u = static_cast<Unet*>(hh);
-  AGPT_CUDA(cudaSetDevice(u->device));
+  DeviceGuard dg_(u->device);
   AGPT_CHECK(N >= 1 && S >= 1, "empty context");
   u->set_context(ctx, N, S, st);
 }
 
 void unet_forward(Handle* hh, const float* x, const int* t_host, int N, int H, int W, float* eps, cudaStream_t st) {
   auto* u = static_cast<Unet*>(hh);
-  AGPT_CUDA(cudaSetDevice(u->device));
+  DeviceGuard dg_(u->device);
   u->forward(x, t_host, N, H, W, eps, st);
 }
 
-// Whole DDIM loop (ddim.py:143-164 + p_sample_ddim): the context holds [uncond ; cond]
-// (2B rows) when cfg_scale != 1, else B rows.
+// Whole DDIM loop (ddim.py:143-164 + p_sample_ddim): the context holds [uncond ; cond] (2B rows) when
+// cfg_scale != 1, else B rows.  Step-invariant work is hoisted: the time-embedding MLP and the 12 ResBlock
+// embedding projections run ONCE for all S timesteps (one GEMM with S rows); step 0 runs eagerly (sizes every
+// buffer), then one step is captured into a CUDA graph and replayed S - 1 times (AGPT_GRAPH=0: plain launches).
 void unet_ddim_sample(Handle* hh, const float* x_T, int B, int H, int W, int S, const int* t_steps,
                       const float* a_t, const float* a_prev, const float* sigma, const float* sqrt_om,
-                      float cfg_scale, float* x_out, cudaStream_t st) {
+                      float cfg_scale, float* x_out, float* pred_x0_out, cudaStream_t st) {
   auto* u = static_cast<Unet*>(hh);
-  AGPT_CUDA(cudaSetDevice(u->device));
+  DeviceGuard dg_(u->device);
   const bool cfg_on = cfg_scale != 1.0f;
   const int N = cfg_on ? 2 * B : B;
   AGPT_CHECK(u->ctxN == N, "agpt_unet_set_context must hold [uncond;cond] (2B rows) for guided sampling, B rows otherwise");
+  for (int i = 0; i < S; ++i) AGPT_CHECK(sigma[i] == 0.f, "the on-device loop is the eta = 0 sampler (noise is drawn by the step-wise path)");
   const long n = (long)u->cfg.in_channels * H * W;
+  u->prepare(N, H, W);
   u->ddim_eps.ensure((size_t)N * n);
-  u->ddim_x.ensure((size_t)N * n);
-  std::vector<int> tt(N);
-  const float* cur = x_T;
+  u->ddim_x.ensure((size_t)B * n);
+  u->ddim_p0.ensure((size_t)B * n);
+  u->emb_table.ensure((size_t)S * u->emb_total);
+  u->emb_cur.ensure((size_t)u->emb_total);
+  u->coef_table.ensure((size_t)S * 6);
+  u->tsteps_dev.ensure((size_t)S);
+  u->step_ctr.ensure(4);
+  // ---- per-call tables (fp32 scalar algebra exactly as torch.full(...).sqrt() would do it, ddim.py:205-224)
+  std::vector<float> coef((size_t)S * 6);
   for (int i = 0; i < S; ++i) {
-    // doubled batch for classifier-free guidance: x_in = cat([x]*2)
-    AGPT_CUDA(cudaMemcpyAsync(u->ddim_x.p, cur, (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (cfg_on)
-      AGPT_CUDA(cudaMemcpyAsync(u->ddim_x.p + (size_t)B * n, cur, (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    for (int j = 0; j < N; ++j) tt[j] = t_steps[i];
-    u->forward(u->ddim_x.p, tt.data(), N, H, W, u->ddim_eps.p, st);
-    ddim_update(cur, u->ddim_eps.p, cfg_on ? 0 : 1, cfg_scale, a_t[i], a_prev[i], sigma[i], sqrt_om[i], nullptr, 1.0f,
-                B, n, x_out, nullptr, st);
-    cur = x_out;
+    float* c = &coef[(size_t)i * 6];
+    c[0] = sqrtf(a_t[i]); c[1] = sqrtf(a_prev[i]); c[2] = sqrtf(1.0f - a_prev[i] - sigma[i] * sigma[i]);
+    c[3] = sigma[i]; c[4] = sqrt_om[i]; c[5] = cfg_scale;
   }
+  AGPT_CUDA(cudaMemcpyAsync(u->coef_table.p, coef.data(), coef.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  AGPT_CUDA(cudaMemcpyAsync(u->tsteps_dev.p, t_steps, (size_t)S * sizeof(int), cudaMemcpyHostToDevice, st));
+  AGPT_CUDA(cudaMemsetAsync(u->step_ctr.p, 0, sizeof(int), st));
+  AGPT_CUDA(cudaStreamSynchronize(st));     // coef / t_steps are caller-owned host memory
+  u->arena_off = 0;
+  {
+    float* te = u->alloc((size_t)S * u->mc);
+    timestep_embedding_dev(te, reinterpret_cast<const int*>(u->tsteps_dev.p), S, u->mc, st);
+    u->embed_rows(te, S, u->emb_table.p, st);
+  }
+  AGPT_CUDA(cudaMemcpyAsync(u->ddim_x.p, x_T, (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+  static int allow_graph = -1;
+  if (allow_graph < 0) { const char* e = getenv("AGPT_GRAPH"); allow_graph = (e && e[0] == '0') ? 0 : 1; }
+  const long l0 = launch_count_now();
+  u->ddim_step(B, N, H, W, n, st);                                   // step 0, eager
+  u->launches_per_step = launch_count_now() - l0;
+  int done = 1;
+  if (allow_graph && S > 1 && !profile_enabled()) {
+    Unet::GraphKey k;
+    k.N = N; k.H = H; k.W = W; k.single = cfg_on ? 0 : 1; k.arena = u->arena.p; k.ctx = u->ctx_kv.p; k.x = u->ddim_x.p; k.ctxS = u->ctxS;
+    const bool same = u->step_graph && k.N == u->gkey.N && k.H == u->gkey.H && k.W == u->gkey.W && k.single == u->gkey.single &&
+                      k.arena == u->gkey.arena && k.ctx == u->gkey.ctx && k.x == u->gkey.x && k.ctxS == u->gkey.ctxS;
+    if (!same) {
+      if (u->step_graph) { cudaGraphExecDestroy(u->step_graph); u->step_graph = nullptr; }
+      cudaGraph_t g = nullptr;
+      // capture on a private stream (the caller's may be the legacy default stream, which cannot capture);
+      // nothing executes during capture, so no ordering with `st` is needed
+      if (!u->cap_stream) AGPT_CUDA(cudaStreamCreateWithFlags(&u->cap_stream, cudaStreamNonBlocking));
+      AGPT_CUDA(cudaStreamBeginCapture(u->cap_stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        u->ddim_step(B, N, H, W, n, u->cap_stream);
+      } catch (...) {
+        cudaStreamEndCapture(u->cap_stream, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+      }
+      AGPT_CUDA(cudaStreamEndCapture(u->cap_stream, &g));
+      const cudaError_t ie = cudaGraphInstantiate(&u->step_graph, g, 0);
+      cudaGraphDestroy(g);
+      AGPT_CUDA(ie);
+      u->gkey = k;
+      count_launch(-u->launches_per_step);       // the captured pass launched nothing
+    }
+    for (; done < S; ++done) AGPT_CUDA(cudaGraphLaunch(u->step_graph, st));
+    count_launch(u->launches_per_step * (S - 1));
+  }
+  for (; done < S; ++done) u->ddim_step(B, N, H, W, n, st);
+  AGPT_CUDA(cudaMemcpyAsync(x_out, u->ddim_x.p, (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (pred_x0_out)
+    AGPT_CUDA(cudaMemcpyAsync(pred_x0_out, u->ddim_p0.p, (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
 }
+
+long unet_launches_per_step(Handle* hh) { return static_cast<Unet*>(hh)->launches_per_step; }
 
 }  // namespace agpt

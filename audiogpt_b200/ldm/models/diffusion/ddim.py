@@ -100,12 +100,18 @@ class DDIMSampler(object):
         self.register_buffer("sqrt_recip_alphas_cumprod", f32((1. / acc).sqrt()))
         self.register_buffer("sqrt_recipm1_alphas_cumprod", f32((1. / acc - 1).sqrt()))
         sig, a, ap = make_ddim_sampling_parameters(acc, self.ddim_timesteps, ddim_eta, verbose)
-        # host-side fp32 tables; per-step scalars are read from these (no device sync)
-        self.ddim_sigmas, self.ddim_alphas, self.ddim_alphas_prev = sig, a, ap
-        self.ddim_sqrt_one_minus_alphas = (1. - a).sqrt()
+        # private host-side fp32 tables: per-step scalars are read from these (no device sync per step) ...
+        self._h_sigmas, self._h_alphas, self._h_alphas_prev = sig, a, ap
+        self._h_sqrt_one_minus_alphas = (1. - a).sqrt()
+        # ... and the reference's registered attributes, on the sampler's device like ddim.py:46-52 keeps them
+        # (external code indexes them with CUDA tensors)
+        self.register_buffer("ddim_sigmas", sig.clone())
+        self.register_buffer("ddim_alphas", a.clone())
+        self.ddim_alphas_prev = ap.double().numpy()        # a float64 numpy array of the fp32 values in the reference too (util.py:66)
+        self.register_buffer("ddim_sqrt_one_minus_alphas", self._h_sqrt_one_minus_alphas.clone())
         acp = self.model.alphas_cumprod_prev.detach().float().cpu()
-        self.ddim_sigmas_for_original_num_steps = ddim_eta * torch.sqrt(
-            (1 - acp) / (1 - acc) * (1 - acc / acp))
+        self._h_sigmas_orig = ddim_eta * torch.sqrt((1 - acp) / (1 - acc) * (1 - acc / acp))
+        self.register_buffer("ddim_sigmas_for_original_num_steps", self._h_sigmas_orig.clone())
 
     # ------------------------------------------------------------------ sampling
     @torch.no_grad()
@@ -138,7 +144,7 @@ class DDIMSampler(object):
             return None
         if quantize_denoised or noise_dropout > 0. or ddim_use_original_steps:
             return None
-        if float(self.ddim_sigmas.abs().max()) != 0.0:      # eta > 0 draws noise per step in torch
+        if float(self._h_sigmas.abs().max()) != 0.0:        # eta > 0 draws noise per step in torch
             return None
         if not torch.is_tensor(cond) or not cond.is_cuda:
             return None
@@ -158,10 +164,13 @@ class DDIMSampler(object):
                               timesteps, ddim_use_original_steps, temperature, unconditional_conditioning,
                               unconditional_guidance_scale)
         if unet is not None:
-            out = self._fused_loop(unet, img, cond, unconditional_conditioning, unconditional_guidance_scale)
-            # the reference logs x at index % log_every_t == 0 and at the first step; with the
-            # loop on device only the end points are available
-            return out, {"x_inter": [img, out], "pred_x0": [img, out]}
+            out, p0 = self._fused_loop(unet, img, cond, unconditional_conditioning, unconditional_guidance_scale)
+            # The reference appends (x, pred_x0) at index % log_every_t == 0 and at the first step
+            # (ddim.py:162-164); with the loop on device only the end points exist: the lists hold the start
+            # and the LAST step's (x_prev, pred_x0) -- the entries callers read ([-1]).  Per-step logging
+            # (any callback / img_callback) selects the step-wise path below, which logs exactly like the
+            # reference.  Note: the on-device loop calls the UNet engine directly, not model.apply_model.
+            return out, {"x_inter": [img, out], "pred_x0": [img, p0]}
 
         if timesteps is None:
             timesteps = self.ddpm_num_timesteps if ddim_use_original_steps else self.ddim_timesteps
@@ -202,13 +211,14 @@ class DDIMSampler(object):
         idx = [S - i - 1 for i in range(S)]
         ci = (C.c_int * S)(*[int(s) for s in order])
         fa = lambda t: (C.c_float * S)(*[float(t[j]) for j in idx])
-        out = torch.empty_like(x)
+        out, p0 = torch.empty_like(x), torch.empty_like(x)
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().agpt_unet_ddim_sample(
-                unet._h, _lib.fptr(x), B, H, W, S, ci, fa(self.ddim_alphas), fa(self.ddim_alphas_prev),
-                fa(self.ddim_sigmas), fa(self.ddim_sqrt_one_minus_alphas),
-                C.c_float(float(scale) if guided else 1.0), _lib.fptr(out), _lib.cur_stream(x.device)))
-        return out
+                unet._h, _lib.fptr(x), B, H, W, S, ci, fa(self._h_alphas), fa(self._h_alphas_prev),
+                fa(self._h_sigmas), fa(self._h_sqrt_one_minus_alphas),
+                C.c_float(float(scale) if guided else 1.0), _lib.fptr(out), _lib.fptr(p0),
+                _lib.cur_stream(x.device)))
+        return out, p0
 
     @torch.no_grad()
     def p_sample_ddim(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,
@@ -241,10 +251,10 @@ class DDIMSampler(object):
         if use_original_steps:
             a_t = float(self.model.alphas_cumprod[index]); a_prev = float(self.model.alphas_cumprod_prev[index])
             sq = float(self.model.sqrt_one_minus_alphas_cumprod[index])
-            sg = float(self.ddim_sigmas_for_original_num_steps[index])
+            sg = float(self._h_sigmas_orig[index])
         else:
-            a_t, a_prev = float(self.ddim_alphas[index]), float(self.ddim_alphas_prev[index])
-            sq, sg = float(self.ddim_sqrt_one_minus_alphas[index]), float(self.ddim_sigmas[index])
+            a_t, a_prev = float(self._h_alphas[index]), float(self._h_alphas_prev[index])
+            sq, sg = float(self._h_sqrt_one_minus_alphas[index]), float(self._h_sigmas[index])
         if not x.is_cuda:
             raise RuntimeError("audiogpt_b200.DDIMSampler runs on CUDA only (no CPU fallback)")
         noise = noise_like(x.shape, device, repeat_noise) if (sg != 0. or noise_dropout > 0.) else None
@@ -267,7 +277,7 @@ class DDIMSampler(object):
         if use_original_steps:
             sa, som = self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod
         else:
-            sa, som = torch.sqrt(self.ddim_alphas).to(x0.device), self.ddim_sqrt_one_minus_alphas.to(x0.device)
+            sa, som = torch.sqrt(self._h_alphas).to(x0.device), self._h_sqrt_one_minus_alphas.to(x0.device)
         if noise is None:
             noise = torch.randn_like(x0)
         shp = (-1,) + (1,) * (x0.dim() - 1)

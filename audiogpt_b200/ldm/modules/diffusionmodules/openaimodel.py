@@ -107,7 +107,10 @@ class UNetModel(nn.Module, _lib.HandleOwner):
             _lib.check(_lib.lib().agpt_unet_set_context(self._h, _lib.fptr(c), c.shape[0], c.shape[1],
                                                          _lib.cur_stream(c.device)))
         self._ctx_key = key
-        self._ctx_keep = c
+        # keep BOTH tensors alive while the key is live: `c` is what the engine read, `context` is what the key
+        # was computed from (when they differ -- fp16 / non-contiguous input -- a freed `context` could hand its
+        # address to another prompt's embedding of the same shape and the stale K/V would be reused)
+        self._ctx_keep = (context, c)
 
     @torch.no_grad()
     def forward(self, x, timesteps=None, context=None, y=None, **kwargs):

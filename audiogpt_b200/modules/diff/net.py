@@ -66,6 +66,9 @@ class DiffNet(nn.Module, _lib.HandleOwner):
             _lib.check(_lib.lib().agpt_diffnet_set_cond(self._h, _lib.fptr(c), c.shape[0], c.shape[2],
                                                          _lib.cur_stream(cond.device)))
         self._cond_key = key
+        # hold the keyed tensor: while it is alive the caching allocator cannot hand its block to the next
+        # utterance's decoder_inp (same B/T/H, version 0), which would make the key match a different cond
+        self._cond_keep = (cond, c)
         self._cond_shape = tuple(c.shape)
 
     @torch.no_grad()

@@ -262,10 +262,50 @@ class GaussianDiffusion(nn.Module):
             self.noise_list = deque(maxlen=4)
             for i in reversed(range(0, t0, pndm_speedup)):
                 x = self.p_sample_plms(x, [i] * b, pndm_speedup, cond)
+        elif self._fast() and x.is_cuda and t0 > 0:
+            x = self._sample_loop_device(x, cond, t0, noises)
         else:
             for i in reversed(range(0, t0)):
                 noise = noises[i] if noises is not None else noise_like(x.shape, x.device, False)
                 x = self._p_sample_core(x, [i] * b, cond, noise)
+        return x
+
+    # per-call budget for pre-drawn noise of the on-device loop (bytes); longer chains run in chunks of steps
+    NOISE_CHUNK_BYTES = 512 << 20
+
+    def _sample_loop_device(self, x, cond, t0, noises):
+        """The ancestral loop inside the library (agpt_gd_sample_loop: one captured step replayed, step tables on
+        the device).  Noise is drawn HERE, one ``noise_like`` call per step in the reference's order (t0-1 .. 0),
+        so a monkey-patched ``noise_like`` and the torch RNG stream see exactly what the step-wise loop shows them."""
+        tb = self._tables()
+        b = x.shape[0]
+        n = x[0].numel()
+        x = x.contiguous().float().clone()
+        self.denoise_fn.set_cond(cond)
+        per_step = b * n * 4
+        chunk = max(1, min(t0, self.NOISE_CHUNK_BYTES // max(per_step, 1)))
+        L = _lib.lib()
+        t_hi = t0
+        while t_hi > 0:
+            t_lo = max(0, t_hi - chunk)
+            ns = t_hi - t_lo
+            if noises is not None and torch.is_tensor(noises) and noises.is_cuda and noises.is_contiguous() \
+                    and noises.dtype == torch.float32:
+                bank = noises[t_lo:t_hi]                      # indexed by t
+            else:
+                bank = torch.empty((ns,) + tuple(x.shape), device=x.device, dtype=torch.float32)
+                for i in reversed(range(t_lo, t_hi)):
+                    bank[i - t_lo].copy_(noises[i] if noises is not None else noise_like(x.shape, x.device, False))
+            coef = np.empty((ns, 5), dtype=np.float32)
+            for k in range(ns):
+                tv = t_hi - 1 - k
+                coef[k] = (tb["A"][tv], tb["B"][tv], tb["c1"][tv], tb["c2"][tv],
+                           float(tb["sigma"][tv]) if tv != 0 else 0.0)
+            with torch.cuda.device(x.device):
+                _lib.check(L.agpt_gd_sample_loop(self.denoise_fn._h, _lib.fptr(x), t_hi, t_lo,
+                                                 coef.ctypes.data_as(C.c_void_p), _lib.fptr(bank),
+                                                 C.c_long(b * n), 1, _lib.cur_stream(x.device)))
+            t_hi = t_lo
         return x
 
     def forward(self, txt_tokens, mel2ph=None, spk_embed=None, ref_mels=None, f0=None, uv=None,

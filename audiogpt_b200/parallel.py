@@ -46,27 +46,74 @@ def shard_range(total: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 def broadcast_state_dict(sd: Dict[str, torch.Tensor], src: int = 0, device=None) -> Dict[str, torch.Tensor]:
-    """One flat fp32 blob, one broadcast.  Every rank passes a dict with the same keys/shapes
-    (contents only matter on ``src``)."""
+    """One flat blob per dtype, one broadcast each (a model's state dict is all-fp32 on this path: one broadcast).
+    Every rank passes a dict with the same keys / shapes / dtypes (contents only matter on ``src``); the
+    agreement is CHECKED with a hash of the (key, shape, dtype) list before any payload moves, and every entry
+    comes back in its own dtype (no silent fp32 round trip for integer buffers or half checkpoints).
+    The engines re-lay the weights out at ``create`` on every rank (deterministic host packing), so what
+    travels is the reference-layout state dict, not the kernel-layout operand images."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return sd
+    import hashlib
     keys = list(sd.keys())
-    sizes = [sd[k].numel() for k in keys]
     dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
                                              if dist.get_backend() == "nccl" else torch.device("cpu"))
-    flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
-    if dist.get_rank() == src:
+    sig = hashlib.sha256(repr([(k, tuple(sd[k].shape), str(sd[k].dtype)) for k in keys]).encode()).digest()[:8]
+    mine = torch.tensor(list(sig), dtype=torch.int64, device=dev)
+    ref = mine.clone()
+    dist.broadcast(ref, src=src)
+    agree = torch.tensor([1 if torch.equal(ref, mine) else 0], dtype=torch.int64, device=dev)
+    dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+    if int(agree.item()) != 1:
+        raise RuntimeError("broadcast_state_dict: ranks disagree on the (key, shape, dtype) list of the state dict")
+    out: Dict[str, torch.Tensor] = {}
+    by_dtype: Dict[torch.dtype, List[str]] = {}
+    for k in keys:
+        by_dtype.setdefault(sd[k].dtype, []).append(k)
+    for dt, ks in by_dtype.items():
+        sizes = [sd[k].numel() for k in ks]
+        flat = torch.empty(sum(sizes), dtype=dt, device=dev)
+        if dist.get_rank() == src:
+            off = 0
+            for k, n in zip(ks, sizes):
+                flat[off:off + n].copy_(sd[k].reshape(-1))
+                off += n
+        dist.broadcast(flat, src=src)
+        flat_cpu = flat.cpu()
         off = 0
-        for k, n in zip(keys, sizes):
-            flat[off:off + n].copy_(sd[k].reshape(-1))
+        for k, n in zip(ks, sizes):
+            out[k] = flat_cpu[off:off + n].reshape(sd[k].shape).clone()
             off += n
-    dist.broadcast(flat, src=src)
-    out, off = {}, 0
-    flat_cpu = flat.cpu()
-    for k, n in zip(keys, sizes):
-        out[k] = flat_cpu[off:off + n].reshape(sd[k].shape).clone()
-        off += n
-    return out
+    return {k: out[k] for k in keys}
+
+
+class AsyncGather:
+    """All-gather of finished per-rank row blocks that stays OFF the compute stream's critical path: ``submit(x)``
+    enqueues ``all_gather_into_tensor`` asynchronously (NCCL's own stream, ordered after the work that produced
+    ``x``), so the gather of batch i overlaps the computation of batch i+1; ``drain()`` makes the current stream
+    wait for everything outstanding and returns the gathered tensors in submission order."""
+
+    def __init__(self):
+        self._pending = []
+
+    def submit(self, x: torch.Tensor):
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            self._pending.append((None, x))
+            return
+        world = dist.get_world_size()
+        x = x.contiguous()
+        out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        work = dist.all_gather_into_tensor(out, x, async_op=True)
+        self._pending.append((work, out, x))
+
+    def drain(self):
+        outs = []
+        for item in self._pending:
+            if item[0] is not None:
+                item[0].wait()          # stream-level wait: the current stream is ordered after the collective
+            outs.append(item[1])
+        self._pending = []
+        return outs
 
 
 def all_gather_rows(x: torch.Tensor, counts: Sequence[int] = None) -> torch.Tensor:

@@ -1,28 +1,32 @@
 #!/usr/bin/env python
 """Benchmark of the AudioGPT generative hot path on B200 (contract: see the task brief).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload hifigan|ddim]
 
-Headline workload (BASELINE.json configs[1], the configuration the metric is quoted on that
-fits one GPU): HiFi-GAN V1 (22.05 kHz, hop 256) vocoding a batch of 8 synthetic 80-bin mels of
-800 frames each -- what `FastSpeech2 TTS -> HiFi-GAN, batch 8` hands to the vocoder.  A step is
-one pass of that batch through `HifiGanGenerator.forward`.  Weights are seeded random of the
-V1 architecture (no checkpoints offline).  Metric: mel-frames/s vocoded (whole job).
+BASELINE.json's metric has two halves; one JSON line carries both:
 
-  value     : device-resident inputs, CUDA-event timed, barrier + synchronize on both sides
-  e2e       : the same metric through the host-buffer C-ABI call
-              (agpt_hifigan_vocode_host: pinned H2D of the mel, forward, D2H of the waveform)
-  roofline  : dominant kernel (tapconv) -- fp32-FMA bound; achieved = algorithmic FLOPs /
-              CUDA-event launch durations measured live; peak = FMA saturation probe run here
-              (the HBM view, as BASELINE asks, is reported beside it against MEASURED_PEAKS.json)
-  cpu_baseline / --impl reference : the CPU oracle (oracle/hifigan_ref.py, a restatement of the
-              reference's forward on torch's own fp32 CPU kernels) on the host cores
-  extra     : clips/s for Make-An-Audio DDIM-100 (C4 per-GPU shard) and utterances/s for the
-              DiffSinger 100-step p_sample chain (C3), each one full un-shortened run
+* top level  -- mel-frames/s vocoded: HiFi-GAN V1 (22.05 kHz, hop 256) on a batch of 8 synthetic 80-bin mels of
+  800 frames per GPU (BASELINE configs[1], what `FastSpeech2 TTS -> HiFi-GAN, batch 8` hands to the vocoder).
+  A step is one pass of that batch through `HifiGanGenerator.forward`.
+* "ddim"     -- clips/s of Make-An-Audio DDIM-100 with classifier-free guidance 1.5 on the C4 shard
+  (BASELINE configs[3]: 32 ten-second clips over 8 GPUs = 4 clips, CFG batch 8, per GPU): every rank runs the
+  whole 100-step chain for its 4 clips, timed on the device, max over ranks; the object has the same fields as
+  the top level (value, ms_per_step, e2e, roofline, gpu_launches, config).  `--workload ddim` prints that object
+  as the line itself.
 
-With N > 1 (torchrun, one rank per GPU) every rank vocodes its own batch of 8 (weak scaling,
-no data-path collective); weights are broadcast once from rank 0 and the finished waveforms
-are all-gathered inside the timed region.
+  value     : device-resident inputs, CUDA-event timed, barrier + synchronize on both sides, max over ranks
+  e2e       : the same metric through the public host-buffer call (pinned H2D of the inputs, D2H of the result
+              inside the timed region): agpt_hifigan_vocode_host / DDIMSampler.sample on host tensors
+  roofline  : the tcgen05 tap-GEMM against the measured bf16/fp16 tensor peak (MEASURED_PEAKS.json).  `frac` is
+              on ALGORITHMIC FLOPs (0.614 GFLOP per mel frame, 18.66 TFLOP per clip); `frac_issued`
+              counts the three fp16 products the error-compensated arithmetic issues per MAC.
+  cpu_baseline / --impl reference : the CPU oracle (oracle/*.py: the reference's forward restated on torch's own
+              fp32 CPU kernels -- the reference is pure Python and does not travel to the GPU box) on the host cores
+  extra     : DiffSinger C3 chain (16 utt x 400 frames x 100 p_sample steps), BigVGAN base, each one full run
+
+With N > 1 (torchrun, one rank per GPU) every rank works on its own batch (weak scaling, no data-path
+collective); weights are broadcast once from rank 0; finished waveforms are all-gathered on NCCL's stream while
+the next batch is computed (the gather of step i overlaps step i+1; the last one is inside the timed region).
 """
 from __future__ import annotations
 
@@ -33,7 +37,6 @@ import statistics
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -45,14 +48,36 @@ import torch  # noqa: E402
 B_PER_GPU, T_FRAMES, HOP, SR = 8, 800, 256, 22050
 METRIC, UNIT = "mel_frames_per_s_vocoded", "frames/s"
 WORKLOAD = "HiFi-GAN V1 22.05kHz vocoder, batch 8 x 800 mel frames per GPU (FastSpeech2->HiFi-GAN, BASELINE configs[1])"
+ARITH = "3xfp16-split: x = hi + lo fp16 parts, products hi*hi + lo*hi + hi*lo on tcgen05 kind::f16, fp32 accumulate in TMEM"
+
+DDIM_B, DDIM_S, DDIM_SCALE, DDIM_SHAPE = 4, 100, 1.5, (4, 10, 78)
+DDIM_METRIC, DDIM_UNIT = "clips_per_s_ddim100_cfg", "clips/s"
+DDIM_WORKLOAD = ("Make-An-Audio txt2audio UNet (160 M params), DDIM-100, eta 0, CFG 1.5, 10 s clips (latent 4x10x78), "
+                 "4 clips per GPU = the 32-clips-over-8-GPUs shard of BASELINE configs[3]")
+DDIM_TFLOP_PER_CLIP = 18.66          # 200 UNet forwards x 93.3 GFLOP
 
 
 def base_config(n_gpus):
     return {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "frames_per_utt": T_FRAMES,
             "global_batch": B_PER_GPU * n_gpus, "hop": HOP, "sample_rate": SR,
-            "weights": "seeded random (specs.synth_hifigan(HIFIGAN_V1, 1234))",
+            "weights": "seeded random (specs.synth_hifigan(HIFIGAN_V1, 1234))", "arith": ARITH,
             "parallelism": f"batch-sharded x{n_gpus}, no data-path collective",
             "l2_policy": "activation working set per step ~2.5 GB >> 126 MB L2 (no explicit flush needed)"}
+
+
+def ddim_config(n_gpus):
+    return {"workload": DDIM_WORKLOAD, "clips_per_gpu": DDIM_B, "global_batch": DDIM_B * n_gpus, "ddim_steps": DDIM_S,
+            "cfg_scale": DDIM_SCALE, "latent": list(DDIM_SHAPE), "context": [77, 1024],
+            "weights": "seeded random (specs.synth_unet(UNET_TXT2AUDIO, 4040))", "arith": ARITH,
+            "parallelism": f"clips sharded x{n_gpus}, no data-path collective",
+            "l2_policy": "weights 641 MB fp32 (1.28 GB as fp16 hi/lo images) re-read every forward >> 126 MB L2"}
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -108,29 +133,34 @@ class ClockSampler:
         return out
 
 
-# ------------------------------------------------------------------------------------ CPU arm
-def cpu_vocode_rate(steps, warmup, batch, frames):
-    """frames/s of the CPU oracle (the reference's forward restated on torch fp32 CPU ops)."""
-    from audiogpt_b200 import specs
-    from oracle import hifigan_ref as hr
+# ------------------------------------------------------------------------------------ CPU arms
+def _calibrate_threads(fn):
+    """torch's intra-op pool scales badly past a few dozen threads on these convs (and torchrun pins
+    OMP_NUM_THREADS=1): time a short sample at several thread counts and keep the best."""
     ncpu = os.cpu_count() or 1
-    h = specs.HIFIGAN_V1
-    sd = specs.synth_hifigan(h, 1234)
-    # give the CPU arm its best thread count: torch's intra-op pool scales badly past a few dozen
-    # threads on these small convs, so calibrate on a short sample instead of blindly using all cores
-    cal = specs.synth_tensor((1, 80, 100), seed=1, scale=2.0, shift=-4.0)
     best, cores = None, ncpu
     for nt in sorted({ncpu, max(1, ncpu // 2), 64, 32, 16, 8}):
         if nt > ncpu:
             continue
         torch.set_num_threads(nt)
-        hr.hifigan_forward(sd, h, cal)
+        fn()
         t0 = time.perf_counter()
-        hr.hifigan_forward(sd, h, cal)
+        fn()
         dt = time.perf_counter() - t0
         if best is None or dt < best:
             best, cores = dt, nt
     torch.set_num_threads(cores)
+    return cores
+
+
+def cpu_vocode_rate(steps, warmup, batch, frames):
+    """frames/s of the CPU oracle (the reference's forward restated on torch fp32 CPU ops)."""
+    from audiogpt_b200 import specs
+    from oracle import hifigan_ref as hr
+    h = specs.HIFIGAN_V1
+    sd = specs.synth_hifigan(h, 1234)
+    cal = specs.synth_tensor((1, 80, 200), seed=1, scale=2.0, shift=-4.0)
+    cores = _calibrate_threads(lambda: hr.hifigan_forward(sd, h, cal))
     mel = specs.synth_tensor((batch, 80, frames), seed=0, scale=2.0, shift=-4.0)
     for _ in range(warmup):
         hr.hifigan_forward(sd, h, mel)
@@ -143,29 +173,158 @@ def cpu_vocode_rate(steps, warmup, batch, frames):
     return batch * frames / sec, sec, cores
 
 
+def cpu_ddim_rate(n_steps_sample):
+    """clips/s of the CPU oracle DDIM-100 + CFG chain at B = 1, from a bounded sample of its 100 steps."""
+    from audiogpt_b200 import specs
+    from oracle import ldm_ref as lr
+    cfg = specs.UNET_TXT2AUDIO
+    sd = specs.synth_unet(cfg, 4040)
+    tab = lr.ldm_schedule()
+    x = torch.tensor(np.random.RandomState(55).randn(1, *DDIM_SHAPE), dtype=torch.float32)
+    c = specs.synth_tensor((1, 77, 1024), seed=5)
+    uc = specs.synth_tensor((1, 77, 1024), seed=6)
+    eps = lambda a, t, ctx: lr.unet_forward(sd, cfg, a, t, ctx)
+    cores = _calibrate_threads(lambda: lr.ddim_sample(eps, tab["alphas_cumprod"], DDIM_S, x, c, uc, DDIM_SCALE, steps_limit=1))
+    t0 = time.perf_counter()
+    lr.ddim_sample(eps, tab["alphas_cumprod"], DDIM_S, x, c, uc, DDIM_SCALE, steps_limit=n_steps_sample)
+    sec_per_step = (time.perf_counter() - t0) / n_steps_sample
+    return 1.0 / (sec_per_step * DDIM_S), sec_per_step, cores
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample of the same workload: 2 of the 8 utterances per step (same T), scaled linearly
+    if args.workload == "ddim":
+        rate, sps, cores = cpu_ddim_rate(max(2, min(args.steps, 6)))
+        sample = (f"B=1: {max(2, min(args.steps, 6))} of the {DDIM_S} DDIM steps (2 UNet forwards each, CFG) on {cores} threads; "
+                  f"clips/s = 1 / (s_per_step x {DDIM_S})")
+        line = {"impl": "reference", "metric": DDIM_METRIC, "value": rate, "unit": DDIM_UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sps * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": ddim_config(args.gpus),
+                "cpu_baseline": {"value": rate, "unit": DDIM_UNIT, "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": rate, "unit": DDIM_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "note": "ms_per_step is one DDIM step of the sample, not one chain"}
+        print(json.dumps(line))
+        return
+    # bounded sample of the same workload: 2 of the 8 utterances per step (same T) in one forward call, as the
+    # reference would run them; the RATE is the result, ms_per_step is the sample's own (not extrapolated)
     sb = 2
     rate, sec, cores = cpu_vocode_rate(args.steps, max(1, min(args.warmup, 2)), sb, T_FRAMES)
-    sample = f"{sb} of {B_PER_GPU} utterances x {T_FRAMES} frames per step, {args.steps} steps, {cores} threads"
+    sample = f"{sb} of {B_PER_GPU} utterances x {T_FRAMES} frames per step ({sb * T_FRAMES} frames), {args.steps} steps, {cores} threads"
+    ddim_rate, ddim_sps, ddim_cores = cpu_ddim_rate(3)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * (B_PER_GPU / sb),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "frames_per_step": sb * T_FRAMES,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": base_config(args.gpus),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-            "note": "CPU oracle port of HifiGanGenerator.forward (the reference is pure PyTorch; /root/reference "
-                    "does not travel to the GPU box); RTF = value*hop/sample_rate"}
+            "ddim": {"impl": "reference", "metric": DDIM_METRIC, "value": ddim_rate, "unit": DDIM_UNIT,
+                     "cpu_baseline": {"value": ddim_rate, "unit": DDIM_UNIT, "cores": ddim_cores, "kind": "port",
+                                      "sample": f"B=1: 3 of the {DDIM_S} DDIM steps (CFG pair per step); clips/s = 1/(s_per_step x {DDIM_S})"},
+                     "s_per_ddim_step": ddim_sps},
+            "note": "CPU oracle port of HifiGanGenerator.forward / DDIMSampler+UNetModel (the reference is pure PyTorch and "
+                    "/root/reference does not travel to the GPU box, so kind = port); ms_per_step and frames_per_step "
+                    "describe the bounded sample actually run; RTF = value*hop/sample_rate"}
     line["x_realtime"] = rate * HOP / SR
     print(json.dumps(line))
 
 
-# ------------------------------------------------------------------------------------ GPU arm
+# ------------------------------------------------------------------------------------ GPU arm: DDIM (C4)
+def measure_ddim(dev, rank, n_gpus, chains, peaks, want_cpu):
+    """All ranks: DDIM-100 + CFG for DDIM_B clips per rank.  Returns the 'ddim' object (rank 0) or None."""
+    import ctypes as C
+    import torch.distributed as dist
+    from audiogpt_b200 import _lib, parallel, specs
+    from audiogpt_b200.ldm.models.diffusion.ddim import DDIMSampler, LatentDiffusionShim
+    from audiogpt_b200.ldm.modules.diffusionmodules.openaimodel import UNetModel
+
+    cfg = specs.UNET_TXT2AUDIO
+    shapes = specs.unet_param_shapes(cfg)
+    sd = specs.synth_unet(cfg, 4040) if rank == 0 else {k: torch.empty(s) for k, s in shapes.items()}
+    sd = parallel.broadcast_state_dict(sd, src=0)
+    u = UNetModel(image_size=32, use_checkpoint=True, **cfg)
+    u.load_state_dict(sd, strict=True)
+    del sd
+    u = u.eval().to(dev)
+    smp = DDIMSampler(LatentDiffusionShim(u).to(dev))
+    B = DDIM_B
+    xT_h = torch.tensor(np.random.RandomState(55 + rank).randn(B, *DDIM_SHAPE), dtype=torch.float32).pin_memory()
+    c_h = specs.synth_tensor((B, 77, 1024), seed=5 + 10 * rank).pin_memory()
+    uc_h = specs.synth_tensor((1, 77, 1024), seed=6).expand(B, -1, -1).contiguous().pin_memory()
+    xT, c, uc = xT_h.to(dev), c_h.to(dev), uc_h.to(dev)
+
+    def chain(x, cc, ucc):
+        z, _ = smp.sample(S=DDIM_S, batch_size=B, shape=DDIM_SHAPE, conditioning=cc, verbose=False, x_T=x, eta=0.0,
+                          unconditional_guidance_scale=DDIM_SCALE, unconditional_conditioning=ucc)
+        return z
+
+    def barrier():
+        if n_gpus > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    chain(xT, c, uc)                                   # warm-up: sizes the arena, captures the step graph
+    barrier()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(chains):
+        z = chain(xT, c, uc)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - l0
+    # e2e: host tensors in, host latent out, through DDIMSampler.sample
+    t0 = time.perf_counter()
+    for _ in range(chains):
+        z_h = chain(xT_h.to(dev, non_blocking=True), c_h.to(dev, non_blocking=True), uc_h.to(dev, non_blocking=True)).cpu()
+    barrier()
+    e2e_sec = (time.perf_counter() - t0) / chains
+    if n_gpus > 1:
+        tt = torch.tensor([ms, e2e_sec], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_sec = float(tt[0].item()), float(tt[1].item())
+    finite = bool(torch.isfinite(z).all().item())
+    L = _lib.lib()
+    L.agpt_unet_launches_per_step.restype = C.c_long
+    lps = int(L.agpt_unet_launches_per_step(u._h))
+    del smp, u
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    ms_chain = ms / chains
+    clips = B * n_gpus
+    value = clips / (ms_chain * 1e-3)
+    ach = DDIM_TFLOP_PER_CLIP * B / (ms_chain * 1e-3)             # per GPU, algorithmic
+    peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+    out = {"metric": DDIM_METRIC, "value": value, "unit": DDIM_UNIT, "n_gpus": n_gpus, "steps": chains, "warmup": 1,
+           "ms_per_step": ms_chain, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": ddim_config(n_gpus),
+           "value_per_gpu": value / n_gpus, "finite": finite,
+           "e2e": {"value": clips / e2e_sec, "unit": DDIM_UNIT,
+                   "h2d_bytes_per_step": int(xT_h.nbytes + c_h.nbytes + uc_h.nbytes), "d2h_bytes_per_step": int(z_h.nbytes),
+                   "api": "DDIMSampler.sample(S=100, ...) on pinned host tensors -> .cpu() latent"},
+           "gpu_launches": int(launches), "launches_per_ddim_step": lps,
+           "roofline": {"kernel": "whole DDIM chain: tcconv5/6 tap-GEMMs + GroupNorm / LayerNorm / attention / update kernels",
+                        "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                        "frac_issued": 3.0 * ach / peak, "algorithmic_tflop_per_clip": DDIM_TFLOP_PER_CLIP,
+                        "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (a kernel timed inside a long step)"
+                                        if peaks else "fallback 1.59 PFLOP/s dense bf16/fp16"),
+                        "note": "achieved = 18.66 algorithmic TFLOP per clip x clips per GPU / chain time (all kernels of the "
+                                "chain, not only the GEMMs); traffic: see profiles/", "traffic": None}}
+    if want_cpu:
+        r, sps, cores = cpu_ddim_rate(3)
+        out["cpu_baseline"] = {"value": r, "unit": DDIM_UNIT, "cores": cores, "kind": "port",
+                               "sample": f"B=1: 3 of the {DDIM_S} DDIM steps of oracle/ldm_ref.py (CFG pair per step) on {cores} threads; "
+                                         f"clips/s = 1 / (s_per_step x {DDIM_S})"}
+    return out
+
+
+# ------------------------------------------------------------------------------------ GPU arm: HiFi-GAN
 def run_ours(args):
+    import ctypes as C
     from audiogpt_b200 import _lib, parallel, specs
     from audiogpt_b200.modules.hifigan.hifigan import HifiGanGenerator
 
@@ -176,7 +335,25 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     import torch.distributed as dist
     L = _lib.lib()
-    L.agpt_fma_peak_tflops.restype = __import__("ctypes").c_double
+    L.agpt_fma_peak_tflops.restype = C.c_double
+    peaks = load_peaks()
+
+    def finish():
+        if n_gpus > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+
+    if args.workload == "ddim":
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        d = measure_ddim(dev, rank, n_gpus, max(1, args.steps), peaks, want_cpu=(n_gpus == 1))
+        if rank == 0:
+            d["clocks"] = sampler.stop()
+            print(json.dumps(d))
+            sys.stdout.flush()
+        finish()
+        return
 
     h = specs.HIFIGAN_V1
     shapes = specs.hifigan_param_shapes(h)
@@ -188,6 +365,7 @@ def run_ours(args):
     mel_host = specs.synth_tensor((B_PER_GPU, 80, T_FRAMES), seed=100 + rank, scale=2.0, shift=-4.0)
     mel = mel_host.to(dev)
     frames_step = B_PER_GPU * T_FRAMES * n_gpus
+    gather = parallel.AsyncGather() if n_gpus > 1 else None
 
     def barrier():
         if n_gpus > 1:
@@ -196,12 +374,14 @@ def run_ours(args):
 
     def step_device():
         wav = model(mel)
-        if n_gpus > 1:
-            wav = parallel.all_gather_rows(wav)             # finished waveforms gathered on every rank
+        if gather is not None:
+            gather.submit(wav)       # finished waveforms -> every rank, on NCCL's stream, under the next step
         return wav
 
     for _ in range(args.warmup):
         step_device()
+    if gather is not None:
+        gather.drain()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -211,6 +391,8 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         step_device()
+    if gather is not None:
+        gather.drain()               # the compute stream waits for every outstanding gather: inside the timed region
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -241,87 +423,93 @@ def run_ours(args):
            "h2d_bytes_per_step": int(mel_np.nbytes), "d2h_bytes_per_step": int(wav_np.nbytes),
            "api": "HifiGanGenerator.vocode_host -> agpt_hifigan_vocode_host (numpy in / numpy out)"}
 
-    if rank != 0:
-        if n_gpus > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
+    # ---- roofline of the dominant kernel, measured live with CUDA events around every launch (rank 0)
+    roofline = None
+    if rank == 0:
+        fma_peak = float(L.agpt_fma_peak_tflops())
+        _lib.check(L.agpt_profile_enable(1))
+        model(mel)
+        msv, flv, byv, lnv = (C.c_double * 4)(), (C.c_double * 4)(), (C.c_double * 4)(), (C.c_longlong * 4)()
+        _lib.check(L.agpt_profile_collect(msv, flv, byv, lnv))
+        _lib.check(L.agpt_profile_enable(0))
+        tot_ms = sum(msv)
+        ach_tf = sum(flv) / (tot_ms * 1e-3) / 1e12
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "tapconv_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        variants = ["fma_BN128", "fma_BN64", "fma_BN32", "tcgen05_3xFP16"]
+        tc_on = lnv[3] > 0
+        per_variant = {variants[i]: {"launches": int(lnv[i]), "ms": msv[i],
+                                     "tflops": (flv[i] / (msv[i] * 1e-3) / 1e12) if msv[i] > 0 else None,
+                                     "gbs": (byv[i] / (msv[i] * 1e-3) / 1e9) if msv[i] > 0 else None}
+                       for i in range(4) if lnv[i] > 0}
+        hbm = {"bound": "hbm", "achieved": sum(byv) / (tot_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+               "frac": sum(byv) / (tot_ms * 1e-3) / 1e9 / hbm_peak,
+               "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
+               "note": "per-launch algorithmic bytes (in+out+residual+weights of every conv launch); the path is compute-bound "
+                       "(AI ~ 10^3 FLOP/B, SURVEY.md 8d) so this fraction is small by construction"}
+        if tc_on:
+            f16_peak = float(peaks.get("bf16_tflops", 1590.0))
+            roofline = {
+                "kernel": "tcconv6_kernel<BN,NI> / tcconv5_kernel<BN,NWK> (tcgen05 tap-GEMM, 3 x fp16 hi/lo products; "
+                          "all contractions of the generator)",
+                "bound": "tensor", "achieved": ach_tf, "peak": f16_peak, "unit": "TFLOP/s",
+                "frac": ach_tf / f16_peak, "frac_issued": 3.0 * ach_tf / f16_peak,
+                "achieved_issued_tflops": 3.0 * ach_tf,
+                "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst: kernels timed one by one); kind::f16 issues at the bf16 rate"
+                                if peaks else "fallback 1.59 PFLOP/s dense bf16/fp16"),
+                "note": "achieved / frac are on ALGORITHMIC FLOPs (SURVEY.md 8d: 0.614 GFLOP per mel frame, zero-padded polyphase "
+                        "taps not counted); the tensor pipe issues 3 fp16 products per fp32-grade MAC (frac_issued)",
+                "fp32_fma_peak_tflops_measured": fma_peak,
+                "algorithmic_vs_fp32_fma_peak": ach_tf / fma_peak if fma_peak > 0 else None,
+                "share_of_step": tot_ms / ms_per_step if n_gpus == 1 else None,
+                "per_variant": per_variant, "hbm": hbm, "traffic": traffic,
+            }
+        else:
+            roofline = {
+                "kernel": "tapconv_kernel<BN> (fp32 FMA; all contractions of the generator)",
+                "bound": "fma_fp32", "achieved": ach_tf, "peak": fma_peak, "unit": "TFLOP/s",
+                "frac": ach_tf / fma_peak if fma_peak > 0 else None,
+                "peak_source": "fp32 FFMA saturation probe run in this process (agpt_fma_peak_tflops)",
+                "share_of_step": tot_ms / ms_per_step if n_gpus == 1 else None,
+                "per_variant": per_variant, "hbm": hbm, "traffic": traffic,
+            }
+    del model
+    torch.cuda.empty_cache()
 
-    # ---- roofline of the dominant kernel, measured live with CUDA events around every launch
-    import ctypes as C
-    fma_peak = float(L.agpt_fma_peak_tflops())
-    _lib.check(L.agpt_profile_enable(1))
-    model(mel)
-    msv, flv, byv, lnv = (C.c_double * 4)(), (C.c_double * 4)(), (C.c_double * 4)(), (C.c_longlong * 4)()
-    _lib.check(L.agpt_profile_collect(msv, flv, byv, lnv))
-    _lib.check(L.agpt_profile_enable(0))
-    tot_ms = sum(msv)
-    ach_tf = sum(flv) / (tot_ms * 1e-3) / 1e12
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "tapconv_traffic.json"))).get("dram_bytes_per_launch")
-    except Exception:
-        pass
-    variants = ["fma_BN128", "fma_BN64", "fma_BN32", "tcgen05_3xFP16"]
-    tc_on = lnv[3] > 0
-    per_variant = {variants[i]: {"launches": int(lnv[i]), "ms": msv[i],
-                                 "tflops": (flv[i] / (msv[i] * 1e-3) / 1e12) if msv[i] > 0 else None,
-                                 "gbs": (byv[i] / (msv[i] * 1e-3) / 1e9) if msv[i] > 0 else None}
-                   for i in range(4) if lnv[i] > 0}
-    hbm = {"bound": "hbm", "achieved": sum(byv) / (tot_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-           "frac": sum(byv) / (tot_ms * 1e-3) / 1e9 / hbm_peak,
-           "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
-           "note": "algorithmic bytes (in+out+residual+weights per launch); the path is compute-bound "
-                   "(AI ~ 10^3 FLOP/B, SURVEY.md 8d) so this fraction is small by construction"}
-    if tc_on:
-        # tcgen05.mma.kind::f16 on fp16 hi/lo operand parts, 3 error-compensated products per algorithmic
-        # MAC: the tensor pipe executes 3x the algorithmic FLOPs.  Denominator: the measured cuBLAS bf16
-        # number (MEASURED_PEAKS.json, burst figure: kernels are timed one by one); fp16 and bf16 issue at
-        # the same rate.
-        f16_peak = float(peaks.get("bf16_tflops", 1590.0))
-        roofline = {
-            "kernel": "tcconv6_kernel<BN,NI> / tcconv5_kernel<BN,NWK> (tcgen05 tap-GEMM, 3 x fp16 hi/lo products; "
-                      "all contractions of the generator)",
-            "bound": "tensor", "achieved": 3.0 * ach_tf, "peak": f16_peak, "unit": "TFLOP/s",
-            "frac": 3.0 * ach_tf / f16_peak,
-            "achieved_algorithmic_tflops": ach_tf,
-            "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst); kind::f16 issues at the bf16 rate" if peaks else
-                            "fallback 1.59 PFLOP/s dense bf16/fp16"),
-            "note": "achieved counts the tensor-pipe FLOPs actually issued (3 fp16 products per fp32-grade MAC); "
-                    "the algorithmic rate is achieved/3",
-            "fp32_fma_peak_tflops_measured": fma_peak,
-            "algorithmic_vs_fp32_fma_peak": ach_tf / fma_peak if fma_peak > 0 else None,
-            "share_of_step": tot_ms / ms_per_step if n_gpus == 1 else None,
-            "per_variant": per_variant, "hbm": hbm, "traffic": traffic,
-        }
-    else:
-        roofline = {
-            "kernel": "tapconv_kernel<BN> (fp32 FMA; all contractions of the generator)",
-            "bound": "fma_fp32", "achieved": ach_tf, "peak": fma_peak, "unit": "TFLOP/s",
-            "frac": ach_tf / fma_peak if fma_peak > 0 else None,
-            "peak_source": "fp32 FFMA saturation probe run in this process (agpt_fma_peak_tflops)",
-            "share_of_step": tot_ms / ms_per_step if n_gpus == 1 else None,
-            "per_variant": per_variant, "hbm": hbm, "traffic": traffic,
-        }
+    # ---- the other half of the metric: DDIM-100 clips/s on the C4 shard (all ranks)
+    ddim = None
+    if not args.no_ddim:
+        try:
+            ddim = measure_ddim(dev, rank, n_gpus, args.ddim_chains, peaks, want_cpu=False)
+        except Exception as ex:
+            if n_gpus > 1:
+                raise
+            ddim = {"error": repr(ex)}
+    if rank != 0:
+        finish()
+        return
 
     # ---- CPU baseline on this box's host cores (bounded sample)
     if n_gpus == 1:
         cb_rate, cb_sec, cores = cpu_vocode_rate(3, 1, 2, T_FRAMES)
         cpu_baseline = {"value": cb_rate, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"2 of {B_PER_GPU} utterances x {T_FRAMES} frames, 1 warm-up + 3 timed passes of "
+                        "sample": f"2 of {B_PER_GPU} utterances x {T_FRAMES} frames in one forward call, 1 warm-up + 3 timed passes of "
                                   f"oracle/hifigan_ref.py on {cores} threads (best of a thread-count calibration; "
                                   f"box has {os.cpu_count()} logical CPUs)"}
+        if ddim and "error" not in ddim:
+            r, sps, dcores = cpu_ddim_rate(3)
+            ddim["cpu_baseline"] = {"value": r, "unit": DDIM_UNIT, "cores": dcores, "kind": "port",
+                                    "sample": f"B=1: 3 of the {DDIM_S} DDIM steps of oracle/ldm_ref.py (CFG pair per step) on "
+                                              f"{dcores} threads; clips/s = 1 / (s_per_step x {DDIM_S})"}
     else:
         cpu_baseline = None   # timed at N=1 only (torchrun pins OMP_NUM_THREADS=1 per rank)
 
     extra = {}
-    if not args.no_extra:
+    if not args.no_extra and n_gpus == 1:
         try:
             extra = extra_metrics(dev)
         except Exception as ex:  # extras must never take the headline down
@@ -333,49 +521,21 @@ def run_ours(args):
             "x_realtime": value * HOP / SR, "x_realtime_per_gpu": value * HOP / SR / n_gpus,
             "tflops_fp32": 0.614e9 * value / 1e12,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "extra": extra}
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "ddim": ddim, "extra": extra}
     print(json.dumps(line))
     sys.stdout.flush()
-    if n_gpus > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    finish()
 
 
 def extra_metrics(dev):
-    """Secondary BASELINE metrics, each one complete run: DDIM-100+CFG clips/s on the C4 per-GPU shard
-    (4 clips -> CFG batch 8 on the 4x10x78 latent) and the C3 DiffSinger chain (16 utt x 400 frames,
-    100 ancestral p_sample steps) -> utterances/s."""
-    from audiogpt_b200 import specs
-    from audiogpt_b200.ldm.models.diffusion.ddim import DDIMSampler, LatentDiffusionShim
-    from audiogpt_b200.ldm.modules.diffusionmodules.openaimodel import UNetModel
+    """Secondary measurements, each one complete run: the C3 DiffSinger chain (16 utt x 400 frames, 100 ancestral
+    p_sample steps on the device loop) -> utterances/s; BigVGAN base (the vocoder Make-An-Audio dispatches)."""
+    import ctypes as C
+    from audiogpt_b200 import _lib, specs
     from audiogpt_b200.modules.diff import shallow_diffusion_tts as sdt
     from audiogpt_b200.modules.diff.net import DiffNet
     from audiogpt_b200.utils.hparams import set_hparams_from_dict
     out = {}
-    # --- C4 shard
-    cfg = specs.UNET_TXT2AUDIO
-    u = UNetModel(image_size=32, use_checkpoint=True, **cfg)
-    u.load_state_dict(specs.synth_unet(cfg, 4040), strict=True)
-    u = u.eval().to(dev)
-    ldm = LatentDiffusionShim(u).to(dev)
-    smp = DDIMSampler(ldm)
-    B = 4
-    xT = torch.tensor(np.random.RandomState(55).randn(B, 4, 10, 78), dtype=torch.float32, device=dev)
-    c = specs.synth_tensor((B, 77, 1024), seed=5).to(dev)
-    uc = specs.synth_tensor((1, 77, 1024), seed=6).expand(B, -1, -1).contiguous().to(dev)
-    smp.sample(S=4, batch_size=B, shape=(4, 10, 78), conditioning=c, verbose=False, x_T=xT,
-               unconditional_guidance_scale=1.5, unconditional_conditioning=uc)          # warm-up
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    z, _ = smp.sample(S=100, batch_size=B, shape=(4, 10, 78), conditioning=c, verbose=False, x_T=xT,
-                      unconditional_guidance_scale=1.5, unconditional_conditioning=uc)
-    torch.cuda.synchronize(dev)
-    dt = time.perf_counter() - t0
-    out["ddim100_cfg1.5_clips_per_s_per_gpu"] = B / dt
-    out["ddim100_seconds_for_4_clips"] = dt
-    out["ddim100_unet_tflops"] = 18.66 * B / dt
-    del u, ldm, smp
-    torch.cuda.empty_cache()
     # --- C3
     cfgd = specs.DIFFNET_BASE
     set_hparams_from_dict(dict(cfgd, keep_bins=80, schedule_type="linear", max_beta=0.06))
@@ -387,15 +547,18 @@ def extra_metrics(dev):
     Bc, Tc = 16, 400
     x = specs.synth_tensor((Bc, 1, 80, Tc), seed=2).to(dev)
     cond = specs.synth_tensor((Bc, 256, Tc), seed=3).to(dev)
-    gd.sample(cond, x_start=x, t_start=3)
+    gd.sample(cond, x_start=x)                         # warm-up (captures the step graph)
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
-    gd.sample(cond, x_start=x)
+    gd.sample(cond, x_start=x)                         # includes drawing the 100 noise tensors, as the reference's loop does
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
     out["diffsinger_c3_utt_per_s"] = Bc / dt
     out["diffsinger_c3_seconds_16utt_100steps"] = dt
-    out["diffsinger_c3_tflops"] = 26.44e6 * Bc * Tc * 100 / dt / 1e12
+    out["diffsinger_c3_tflops_algorithmic"] = 26.44e6 * Bc * Tc * 100 / dt / 1e12
+    Lb = _lib.lib()
+    Lb.agpt_diffnet_launches_per_step.restype = C.c_long
+    out["diffsinger_c3_launches_per_step"] = int(Lb.agpt_diffnet_launches_per_step(net._h))
     del net, gd
     torch.cuda.empty_cache()
     # --- BigVGAN ("next" row 8f-2: the vocoder Make-An-Audio actually dispatches), base 22 kHz / 80-band topology
@@ -427,9 +590,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-extra", action="store_true", help="skip the secondary DDIM / DiffSinger measurements")
+    ap.add_argument("--workload", default="hifigan", choices=["hifigan", "ddim"],
+                    help="hifigan (default): the contract line, with the DDIM C4 measurement under 'ddim'; "
+                         "ddim: the C4 DDIM-100 line alone (steps = timed chains)")
+    ap.add_argument("--ddim-chains", type=int, default=2, help="timed DDIM-100 chains of the 'ddim' object (after 1 warm-up chain)")
+    ap.add_argument("--no-ddim", action="store_true", help="skip the DDIM C4 measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary DiffSinger / BigVGAN measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.workload == "ddim" and args.impl == "ours":
+        args.steps = min(args.steps, 5)
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -124,6 +124,16 @@ int agpt_diffnet_eps(agpt_handle h, const float* x, const int* t_host, float* ep
 int agpt_gd_p_sample(agpt_handle h_or_null, const float* x, const float* eps_or_null, const int* t_host,
                      const float* coef_host /*[B][5]*/, const float* noise_or_null, int clip_denoised,
                      int B, long n_per_sample, float* x_out, void* stream);
+/* The whole ancestral loop of GaussianDiffusion.forward(infer=True) (shallow_diffusion_tts.py:263-272) on the
+ * device: for t = t_hi-1 .. t_lo: x_io <- p_sample(x_io, t, noises[t - t_lo]) with every sample at the same t, the
+ * DiffNet handle `h` (cond set by agpt_diffnet_set_cond) predicting eps.  coef_host [t_hi-t_lo][5]: the rows of
+ * agpt_gd_p_sample in SAMPLING order (row k belongs to t = t_hi-1-k).  noises_or_null: device
+ * [t_hi-t_lo][noise_step_stride] floats, pre-drawn by the caller in the reference's RNG call order.  The
+ * step-embedding MLP and the per-layer diffusion projections run once for all steps; step 0 runs as plain
+ * launches, then ONE captured step (CUDA graph + device-side step counter) is replayed.  AGPT_GRAPH=0 disables. */
+int agpt_gd_sample_loop(agpt_handle h, float* x_io, int t_hi, int t_lo, const float* coef_host,
+                        const float* noises_or_null, long noise_step_stride, int clip_denoised, void* stream);
+long agpt_diffnet_launches_per_step(agpt_handle h);
 /* generic elementwise: out = a0*x + a1*e0 + a2*e1 + a3*e2 + a4*e3 (per-sample
  * coefficient rows coef_host[B][5]; NULL e_i are skipped) -- the PLMS
  * combinations of shallow_diffusion_tts.py:174-204.                          */
@@ -163,13 +173,20 @@ int agpt_ddim_update(const float* x, const float* eps2, int eps2_is_single, floa
                      float a_t, float a_prev, float sigma_t, float sqrt_one_minus_at,
                      const float* noise, float temperature, int B, long n_per_sample,
                      float* x_prev, float* pred_x0_or_null, void* stream);
-/* Whole DDIM loop on device (ddim.py:117-166) with CFG; context = [uncond ; cond]
+/* Whole DDIM loop on device (ddim.py:117-166, eta = 0) with CFG; context = [uncond ; cond]
  * set through agpt_unet_set_context (2B rows) or B rows when cfg_scale == 1.
- * tables: host arrays of length S in *sampling order* (index S-1 first).     */
+ * tables: host arrays of length S in *sampling order* (index S-1 first).  The time-embedding
+ * MLP and the ResBlock embedding projections run once for all S timesteps; step 0 runs as plain
+ * launches, then ONE captured step (CUDA graph, device-side step counter and coefficient tables)
+ * is replayed S-1 times; the step's x_prev update reads its scalars from the table (no host sync,
+ * no per-step H2D).  pred_x0_or_null receives the last step's pred_x0 (ddim.py:216).
+ * AGPT_GRAPH=0 in the environment replaces the replays by plain launches.                     */
 int agpt_unet_ddim_sample(agpt_handle h, const float* x_T, int B, int H, int W, int S,
                           const int* t_steps_host, const float* a_t, const float* a_prev,
                           const float* sigma, const float* sqrt_om, float cfg_scale,
-                          float* x_out, void* stream);
+                          float* x_out, float* pred_x0_or_null, void* stream);
+/* kernels launched per DDIM step by the last agpt_unet_ddim_sample call (bench.py reports it) */
+long agpt_unet_launches_per_step(agpt_handle h);
 
 #ifdef __cplusplus
 }

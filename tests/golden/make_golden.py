@@ -248,6 +248,48 @@ def golden_diffusion():
     save("diffusion_base_fwd", eps=eb)
 
 
+def golden_c3_full():
+    """BASELINE configs[2] at full size: DiffNet base (20 x 256), B=16, T=400, 100 ancestral p_sample steps
+    with the per-step noise of SURVEY.md 8d (seed 4), run by the reference's own GaussianDiffusion."""
+    from utils.hparams import hparams
+    hparams.clear()
+    cfgb = specs.DIFFNET_BASE
+    hparams.update(hidden_size=cfgb["hidden_size"], residual_layers=cfgb["residual_layers"],
+                   residual_channels=cfgb["residual_channels"],
+                   dilation_cycle_length=cfgb["dilation_cycle_length"],
+                   keep_bins=80, schedule_type="linear", max_beta=0.06)
+    from modules.diff.net import DiffNet
+    import modules.diff.shallow_diffusion_tts as sdt
+
+    class _NoFS2(torch.nn.Module):
+        def __init__(self, *a, **k):
+            super().__init__()
+
+    sdt.FastSpeech2 = _NoFS2
+    sdt.FastSpeech2MIDI = _NoFS2
+    net = DiffNet(80)
+    net.load_state_dict(specs.synth_diffnet(cfgb, 2025), strict=True)
+    net.eval()
+    gd = sdt.GaussianDiffusion(None, 80, net, timesteps=100, K_step=100, loss_type="l1",
+                               betas=sdt.linear_beta_schedule(100, 0.06),
+                               spec_min=specs.SPEC_MIN, spec_max=specs.SPEC_MAX)
+    gd.eval()
+    B, T = 16, 400
+    x = specs.synth_tensor((B, 1, 80, T), seed=2)
+    cond = specs.synth_tensor((B, 256, T), seed=3)
+    cur = {"i": 0}
+    sdt.noise_like = lambda shape, device, repeat=False: specs.synth_tensor((B, 1, 80, T), seed=4000 + cur["i"])
+    import time
+    t0 = time.time()
+    for i in reversed(range(100)):
+        cur["i"] = i
+        x = gd.p_sample(x, torch.full((B,), i, dtype=torch.long), cond)
+        if i % 10 == 0:
+            print(f"  c3 step {i}: rms {x.pow(2).mean().sqrt().item():.4f}  ({time.time() - t0:.0f} s)", flush=True)
+    mel = gd.denorm_spec(x[:, 0].transpose(1, 2))
+    save("diffusion_c3_full", x_end=x[:, :, :, ::4], mel_end=mel[:, ::4, :], stats=stats(x))
+
+
 # --------------------------------------------------------------------------- Make-An-Audio
 def import_ldm():
     oc = types.ModuleType("omegaconf")
@@ -281,7 +323,7 @@ class LDMShim:
         return self.unet(x, timesteps=t, context=c)
 
 
-def golden_ldm():
+def golden_ldm(only100=False):
     from ldm.modules.diffusionmodules.openaimodel import UNetModel
     from ldm.modules.diffusionmodules.util import make_beta_schedule
     from ldm.models.diffusion.ddim import DDIMSampler
@@ -299,6 +341,12 @@ def golden_ldm():
         u.eval()
         return u
 
+    if not only100:
+        _golden_ldm_small(build, tab, DDIMSampler)
+    _golden_ldm_full(build, tab, DDIMSampler, only100)
+
+
+def _golden_ldm_small(build, tab, DDIMSampler):
     # ---- small UNet: forward + DDIM-10 with CFG ---------------------------------------
     cfg = specs.UNET_SMALL
     u = build(cfg, 3030)
@@ -327,6 +375,9 @@ def golden_ldm():
          **tabs10,
          alphas_cumprod=tab["alphas_cumprod"])
 
+
+
+def _golden_ldm_full(build, tab, DDIMSampler, only100):
     # ---- full txt2audio UNet (C4 shape): one CFG-pair forward + DDIM-100 first 4 steps --
     cfgf = specs.UNET_TXT2AUDIO
     uf = build(cfgf, 4040)
@@ -346,7 +397,15 @@ def golden_ldm():
         img, _ = smpf.p_sample_ddim(img, cf, ts, index=idx, unconditional_guidance_scale=1.5,
                                     unconditional_conditioning=ucf)
     print("ddim full 4 steps rms", img.pow(2).mean().sqrt().item())
-    save("ldm_txt2audio", eps_pair=ef, ddim100_first4=img)
+    if not only100:
+        save("ldm_txt2audio", eps_pair=ef, ddim100_first4=img)
+
+    # ---- the whole DDIM-100 + CFG 1.5 chain (C4 per-clip work, B=1): end point and last pred_x0 ----
+    out100, inter100 = smpf.sample(S=100, batch_size=1, shape=(4, 10, 78), conditioning=cf, verbose=False,
+                                   unconditional_guidance_scale=1.5, unconditional_conditioning=ucf,
+                                   eta=0.0, x_T=xf)
+    print("ddim-100 end point rms", out100.pow(2).mean().sqrt().item(), "absmax", out100.abs().max().item())
+    save("ldm_txt2audio_ddim100", x_T=xf, ddim100=out100, pred_x0_last=inter100["pred_x0"][-1])
 
 
 def golden_bigvgan():
@@ -397,8 +456,8 @@ def golden_vae():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["hifigan", "diffusion", "ldm", "bigvgan", "vae"]
-    if "hifigan" in which or "diffusion" in which:
+    which = sys.argv[1:] or ["hifigan", "diffusion", "c3", "ldm", "bigvgan", "vae"]   # extra selector: ldm100 (DDIM-100 end point only)
+    if "hifigan" in which or "diffusion" in which or "c3" in which:
         import_neuralseq()
         cwd = os.getcwd()
         os.chdir(os.path.join(REF, "NeuralSeq"))
@@ -407,16 +466,18 @@ if __name__ == "__main__":
                 golden_hifigan()
             if "diffusion" in which:
                 golden_diffusion()
+            if "c3" in which:
+                golden_c3_full()
         finally:
             os.chdir(cwd)
-    if "ldm" in which:
+    if "ldm" in which or "ldm100" in which:
         # drop NeuralSeq's top-level packages so that Make-An-Audio's resolve
         for k in [k for k in sys.modules if k.split(".")[0] in ("modules", "utils", "vocoders", "tasks")]:
             del sys.modules[k]
         if os.path.join(REF, "NeuralSeq") in sys.path:
             sys.path.remove(os.path.join(REF, "NeuralSeq"))
         import_ldm()
-        golden_ldm()
+        golden_ldm(only100="ldm" not in which)
     if "bigvgan" in which:
         for k in [k for k in sys.modules if k.split(".")[0] in ("modules", "utils", "vocoders", "tasks")]:
             del sys.modules[k]

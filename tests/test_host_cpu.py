@@ -141,8 +141,8 @@ def test_ddim_tables_match_oracle():
     s.make_schedule(100, ddim_eta=0.0, verbose=False)
     tab = lr.ddim_tables(lr.ldm_schedule()["alphas_cumprod"], 100)
     assert np.array_equal(s.ddim_timesteps, tab["timesteps"]) and s.ddim_timesteps[0] == 1 and s.ddim_timesteps[-1] == 991
-    assert torch.equal(s.ddim_alphas, torch.as_tensor(tab["alphas"]))
-    assert np.array_equal(s.ddim_alphas_prev.double().numpy(), np.asarray(tab["alphas_prev"], dtype=np.float64))
+    assert torch.equal(s.ddim_alphas.cpu(), torch.as_tensor(tab["alphas"]))
+    assert np.array_equal(np.asarray(s.ddim_alphas_prev, dtype=np.float64), np.asarray(tab["alphas_prev"], dtype=np.float64))
 
 
 def test_shard_range_and_lpt():
@@ -177,6 +177,24 @@ allw = parallel.all_gather_rows(mine, counts=[3, 2])
 assert allw.shape == (5, 1, 7) and torch.equal(allw[:, 0, 0], torch.arange(5.0))
 eq = parallel.all_gather_rows(torch.full((2, 3), float(rank)))
 assert eq.shape == (4, 3) and eq[0, 0] == 0 and eq[3, 0] == 1
+# mixed dtypes keep their dtype and value (ADVICE r1): an int64 buffer above 2^24 and a half tensor
+mixed = {{"w": torch.full((3,), 1.5 if rank == 0 else 0.0), "n": torch.tensor([2 ** 40 + 1 if rank == 0 else 0]),
+         "h": torch.full((2,), 0.25 if rank == 0 else 0.0, dtype=torch.float16)}}
+got = parallel.broadcast_state_dict(mixed, src=0)
+assert got["n"].dtype == torch.int64 and int(got["n"][0]) == 2 ** 40 + 1 and got["h"].dtype == torch.float16
+assert float(got["w"][0]) == 1.5 and float(got["h"][1]) == 0.25 and list(got) == ["w", "n", "h"]
+# disagreement on the key/shape list is detected on every rank instead of silently mis-slicing the blob
+bad = {{"w": torch.zeros(3 + rank)}}
+try:
+    parallel.broadcast_state_dict(bad, src=0)
+    raise SystemExit("shape mismatch not detected")
+except RuntimeError as ex:
+    assert "disagree" in str(ex)
+# asynchronous gather (the bench's waveform all-gather): two batches in flight, drained in order
+ag = parallel.AsyncGather()
+ag.submit(torch.full((2, 4), 10.0 + rank)); ag.submit(torch.full((1, 4), 20.0 + rank))
+g0, g1 = ag.drain()
+assert g0.shape == (4, 4) and g0[0, 0] == 10 and g0[3, 0] == 11 and g1.shape == (2, 4) and g1[1, 0] == 21
 # mixed dispatch (BASELINE configs[4]): LPT assignment, every job exactly once, one all_gather of timings
 import time
 jobs = [("tts", 200 + 37 * i) for i in range(6)] + [("t2a", 0)] * 2

@@ -160,6 +160,45 @@ def test_unet_txt2audio_forward():
     assert rel_rmse(out, g["ddim100_first4"]) < 1e-4
 
 
+def test_ddim100_full_chain():
+    """The oracle's whole DDIM-100 + CFG chain (200 forwards of the 160 M-param UNet, B = 1) against the end point of
+    the reference's own sampler (fixture made by `make_golden.py ldm100`).  This also measures how much this chain
+    amplifies a 1e-6-level perturbation (different summation order only): the GPU gate in test_ldm_gpu.py is set
+    from it."""
+    g = load_golden("ldm_txt2audio_ddim100")
+    cfg = specs.UNET_TXT2AUDIO
+    sd = specs.synth_unet(cfg, 4040)
+    cf = specs.synth_tensor((1, 77, 1024), seed=5)
+    ucf = specs.synth_tensor((1, 77, 1024), seed=6)
+    sch = lr.ldm_schedule()
+    fn = lambda x, t, c: lr.unet_forward(sd, cfg, x, t, c)
+    out = lr.ddim_sample(fn, sch["alphas_cumprod"], 100, T(g["x_T"]), cf, ucf, 1.5)
+    e = rel_rmse(out, g["ddim100"])
+    print("oracle DDIM-100 end point rel-RMSE vs reference:", e)
+    assert e < 1e-4
+
+
+def test_c3_full_chain():
+    """The oracle's full-size C3 chain (DiffNet 20 x 256, B = 16, T = 400, 100 ancestral steps) against the
+    reference's own GaussianDiffusion (fixture made by `make_golden.py c3`)."""
+    g = load_golden("diffusion_c3_full")
+    cfg = specs.DIFFNET_BASE
+    sd = specs.synth_diffnet(cfg, 2025)
+    tab = dr.schedule_tables(dr.linear_betas(100, 0.06))
+    B, Tn = 16, 400
+    x = specs.synth_tensor((B, 1, 80, Tn), seed=2)
+    cond = specs.synth_tensor((B, 256, Tn), seed=3)
+    fn = lambda a, b, c: dr.diffnet_forward(sd, cfg, a, b, c)
+    for i in reversed(range(100)):
+        x = dr.p_sample(tab, fn, x, torch.full((B,), i, dtype=torch.long), cond,
+                        specs.synth_tensor((B, 1, 80, Tn), seed=4000 + i))
+    e = rel_rmse(x[:, :, :, ::4], g["x_end"])
+    print("oracle C3 full chain rel-RMSE vs reference:", e)
+    assert e < 1e-4
+    smin, smax = T(specs.SPEC_MIN)[None, None], T(specs.SPEC_MAX)[None, None]
+    assert rel_rmse(dr.denorm_spec(x[:, 0].transpose(1, 2), smin, smax)[:, ::4, :], g["mel_end"]) < 1e-4
+
+
 def test_bigvgan_small():
     """oracle/bigvgan_ref.py == the reference's BigVGAN module (fixture made by make_golden.py bigvgan)."""
     from oracle import bigvgan_ref as br
