@@ -200,4 +200,13 @@ int agpt_bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wrea
   return guarded([&] { bench_tapconv(G, L, Cin, Cout, K, dil, Wreal, epi_res, use_tc, reps, check, out3, dbg8_or_null); });
 }
 
+int agpt_check_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, int epi_res, double x_scale,
+                       double w_spread, double* rel2) {
+  return guarded([&] {
+    AGPT_CHECK(rel2, "null argument");
+    double out3[3];
+    bench_tapconv(G, L, Cin, Cout, K, dil, Wreal, epi_res, 1, 1, 1, out3, nullptr, x_scale, w_spread, rel2);
+  });
+}
+
 }  // extern "C"

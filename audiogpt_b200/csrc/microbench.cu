@@ -9,19 +9,26 @@ namespace agpt {
 // out[0] = ms per launch, out[1] = TFLOP/s (algorithmic), out[2] = max |tc - fma| (when check != 0)
 // dbg_avg[8]: averaged phase deltas in cycles (setup, first-A, mainloop, tail, epilogue, total, waitA, waitW)
 void bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, int epi_res, int use_tc, int reps,
-                   int check, double* out, double* dbg_avg) {
+                   int check, double* out, double* dbg_avg, double x_scale, double w_spread, double* rel2) {
   std::mt19937 rng(1234);
   std::normal_distribution<float> nd(0.f, 1.f);
   const bool is2d = Wreal > 0;
   const int taps = is2d ? 9 : K;
   std::vector<float> w((size_t)Cout * Cin * taps), b(Cout);
   for (auto& v : w) v = nd(rng) / std::sqrt((float)Cin * taps);
+  if (w_spread > 1.0) {   // weight-norm-like gain spread: output channel co scaled by w_spread^u, u log-uniform in [-1/2, 1/2]
+    std::uniform_real_distribution<float> ud(-0.5f, 0.5f);
+    for (int co = 0; co < Cout; ++co) {
+      const float gsc = std::pow((float)w_spread, ud(rng));
+      for (size_t i = 0; i < (size_t)Cin * taps; ++i) w[(size_t)co * Cin * taps + i] *= gsc;
+    }
+  }
   for (auto& v : b) v = 0.05f * nd(rng);
   PackedConv pc;
   pack_conv(pc, w.data(), b.data(), Cout, Cin, taps, is2d);
   const size_t nin = (size_t)G * L * Cin, nout = (size_t)G * L * Cout;
   std::vector<float> hx(nin);
-  for (auto& v : hx) v = nd(rng);
+  for (auto& v : hx) v = nd(rng) * (float)x_scale;
   DevBuf x, y, y2, r;
   x.upload(hx);
   y.ensure(nout); y2.ensure(nout); r.ensure(nout);
@@ -94,9 +101,19 @@ void bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, i
     std::vector<float> a(nout), c(nout);
     AGPT_CUDA(cudaMemcpy(a.data(), y.p, nout * 4, cudaMemcpyDeviceToHost));
     AGPT_CUDA(cudaMemcpy(c.data(), y2.p, nout * 4, cudaMemcpyDeviceToHost));
-    double mx = 0;
-    for (size_t i = 0; i < nout; ++i) mx = std::max(mx, (double)std::fabs(a[i] - c[i]));
+    double mx = 0, se = 0, sr = 0;
+    bool finite = true;
+    for (size_t i = 0; i < nout; ++i) {
+      const double d = (double)a[i] - (double)c[i];
+      if (!std::isfinite(a[i])) finite = false;
+      mx = std::max(mx, std::fabs(d)); se += d * d; sr += (double)c[i] * c[i];
+    }
     out[2] = mx;
+    if (rel2) {   // {max |diff| / rms(reference), rms(diff) / rms(reference)}; reference = the fp32-FMA kernel
+      const double rms = std::sqrt(sr / (double)nout);
+      rel2[0] = finite ? (rms > 0 ? mx / rms : mx) : 1e30;
+      rel2[1] = finite ? (rms > 0 ? std::sqrt(se / (double)nout) / rms : std::sqrt(se / (double)nout)) : 1e30;
+    }
   }
   tc_set_enabled(tc_prev ? 1 : 0);
   cudaEventDestroy(e0); cudaEventDestroy(e1);

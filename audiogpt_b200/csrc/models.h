@@ -35,6 +35,6 @@ void unet_ddim_sample(Handle* h, const float* x_T, int B, int H, int W, int S, c
 long unet_launches_per_step(Handle* h);
 
 void bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, int epi_res, int use_tc, int reps,
-                   int check, double* out, double* dbg_avg);
+                   int check, double* out, double* dbg_avg, double x_scale = 1.0, double w_spread = 1.0, double* rel2 = nullptr);
 
 }  // namespace agpt

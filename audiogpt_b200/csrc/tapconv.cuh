@@ -54,17 +54,16 @@ struct TapConvParams {
   int epi; const float* res; long res_gstride; int res_pitch; float scale; int accumulate;
   const float* evec; int evec_gstride;
   float* out2; long out2_gstride; int out2_pitch; int csplit;
-  const float* w_tc256;   // optional BN=256 image (layers with Cout % 256 == 0)
   const float* w_h; const float* w_h256; const float* w_h64; int tc_chunks_h; float tc_descale;   // fp16 hi/lo image (tcconv5.cu): 64-channel chunks, weights pre-scaled by 1/tc_descale
-  const float* w_tc; int tc_bn, tc_chunks, tc_na, tc_nw, tc_nr, tc_nwk, tc_nb, tc_tps, tc_flags, tc_flags_user;
-  long long* dbg;      // optional per-CTA phase timestamps (tc_flags & 2)   // tensor-core weight image (tcconv.cu); tc_bn == 0 => FMA only
+  int tc_bn, tc_na, tc_nw, tc_nr, tc_nwk, tc_nb, tc_tps, tc_flags, tc_flags_user;   // tc_bn == 0 => FMA only
+  long long* dbg;      // optional per-CTA phase timestamps (tc_flags & 2)
   float flops_scale;   // useful fraction of the MACs (zero-padded polyphase taps); 0 => 1
 };
 
 // ---------------------------------------------------------------- host side
 struct PackedConv {
-  DevBuf w, b, w_tc, w_tc256, w_h, w_h256, w_h64;
-  int tc_bn = 0, tc_chunks = 0, h_chunks = 0;
+  DevBuf w, b, w_h, w_h256, w_h64;
+  int tc_bn = 0, h_chunks = 0;
   float h_descale = 1.f;
   int Cin = 0, cin_pad = 0, Cout = 0, cout_pad = 0, ntaps = 0;
   int tap_off_1d[kMaxTaps] = {0};   // for 1-D convs: row offsets; 2-D convs derive offsets from W at launch
@@ -83,9 +82,7 @@ inline int tc_pick_bn(int cout) {
 struct PackedConv;
 // Fill geometry-dependent fields (offsets, halo, smem rows) and launch (tapconv.cu).
 void tapconv_launch(TapConvParams P, cudaStream_t st);
-void tcconv_launch(TapConvParams P, cudaStream_t st);          // tcgen05 version (tcconv.cu / tcconv2.cu)
-bool tcconv2_launch(TapConvParams P, cudaStream_t st);
-bool tcconv3_launch(TapConvParams P, cudaStream_t st);
+void tcconv_launch(TapConvParams P, cudaStream_t st);          // tcgen05 dispatcher (tcconv.cu)
 bool tcconv5_launch(TapConvParams P, cudaStream_t st);
 bool tcconv6_launch(TapConvParams P, cudaStream_t st, bool force);
 struct HTile { int bn; const float* w; long ntiles; };
@@ -121,7 +118,7 @@ inline TapConvParams tapconv_params(const PackedConv& pc, int G, int L, int Wrea
   }
   P.scale = 1.f;
   P.flops_scale = pc.useful;
-  P.w_tc = pc.w_tc.p; P.tc_bn = pc.tc_bn; P.tc_chunks = pc.tc_chunks; P.w_tc256 = pc.w_tc256.p;
+  P.tc_bn = pc.tc_bn;
   P.w_h = pc.w_h.p; P.w_h256 = pc.w_h256.p; P.w_h64 = pc.w_h64.p; P.tc_chunks_h = pc.h_chunks; P.tc_descale = pc.h_descale;
   return P;
 }

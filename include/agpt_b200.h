@@ -38,11 +38,13 @@ int agpt_profile_collect(double ms[4], double flops[4], double bytes[4], long lo
 /* dev tooling: one text line per recorded launch ("variant G L Cin Cout ntaps span epi Wreal ms flops"); returns bytes written or -1 */
 long agpt_profile_dump(char* out, long cap);
 double agpt_fma_peak_tflops(void);
-/* 1 (default): contractions run on tcgen05 tensor cores with 3xTF32 error compensation;
- * 0: fp32-FMA kernels only (bit-for-bit the round-1 numerics).                            */
+/* 1 (default): contractions run on the tcgen05 tensor cores with error-compensated fp16 parts
+ * ("3xfp16": x = hi + lo, products hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM; weights pre-scaled
+ * by a power of two per layer); 0: the fp32-FMA kernels only.  Environment: AGPT_TENSOR_CORES.        */
 int agpt_set_tensor_cores(int on);
-/* tcgen05 kernel generation: 1 = per-tap operand tiles, 2 = shifted-descriptor taps (default),
- * 3 = persistent for k >= 5, 4 = persistent everywhere (experimental); -1 = environment/default. */
+/* tcgen05 kernel schedule: 6 (default) = persistent kernel (tcconv6) where a CTA gets more than one tile,
+ * one-tile-per-CTA kernel (tcconv5) otherwise; 5 = tcconv5 only; 7 = tcconv6 forced; -1 = environment
+ * (AGPT_TC_V) / default.                                                                               */
 int agpt_set_tc_version(int v);
 /* Micro-benchmark of one tapconv layer (random data): out3 = {ms per launch, algorithmic TFLOP/s,
  * max |tcgen05 - fp32 FMA| when check != 0}; dbg8 (tcgen05 only) = average per-CTA phase cycles
@@ -50,6 +52,11 @@ int agpt_set_tc_version(int v);
  * wait-on-weights}.  Wreal > 0 selects a 3x3 conv on an (L/Wreal) x Wreal image.              */
 int agpt_bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, int epi_res, int use_tc,
                        int reps, int check, double* out3, double* dbg8_or_null);
+/* Numerics probe of one layer: activations ~ N(0,1) * x_scale, weights with a weight-norm-like gain spread
+ * (output channel gains log-uniform over a factor w_spread); runs the selected tcgen05 kernel and the fp32-FMA
+ * kernel on the same data.  rel2 = {max |diff| / rms(ref), rms(diff) / rms(ref)} (1e30 if anything is not finite). */
+int agpt_check_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, int epi_res, double x_scale,
+                       double w_spread, double* rel2);
 
 /* ------------------------------------------------------------------ HiFi-GAN
  * Replaces HifiGanGenerator.__init__/forward/remove_weight_norm

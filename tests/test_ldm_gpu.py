@@ -27,7 +27,7 @@ def test_state_dict_keys_match_reference_layout():
     assert keys == list(specs.unet_param_shapes(cfg).keys())
     assert "input_blocks.1.1.transformer_blocks.0.attn2.to_k.weight" in keys
     assert "output_blocks.2.2.conv.weight" in keys and "input_blocks.3.0.op.weight" in keys
-    assert sum(p.numel() for p in u.parameters()) == 160_218_884
+    assert sum(p.numel() for p in u.parameters()) == 160_223_684
 
 
 def test_unet_small_forward():
