@@ -49,6 +49,12 @@ class UnetCfg(C.Structure):
                 ("transformer_depth", C.c_int), ("context_dim", C.c_int)]
 
 
+class VaeCfg(C.Structure):
+    _fields_ = [("embed_dim", C.c_int), ("z_channels", C.c_int), ("ch", C.c_int), ("out_ch", C.c_int),
+                ("num_levels", C.c_int), ("ch_mult", C.c_int * AGPT_MAX_LEVELS), ("num_res_blocks", C.c_int),
+                ("attn_at_level", C.c_int * AGPT_MAX_LEVELS)]
+
+
 _lock = threading.Lock()
 _lib = None
 

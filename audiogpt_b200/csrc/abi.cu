@@ -195,6 +195,21 @@ long agpt_unet_launches_per_step(agpt_handle h) {
   return n;
 }
 
+int agpt_vae_create(const agpt_vae_cfg* cfg, const float* const* host_weights, int n_weights, int device,
+                    agpt_handle* out) {
+  return guarded([&] {
+    AGPT_CHECK(cfg && host_weights && out, "null argument");
+    *out = reinterpret_cast<agpt_handle>(vae_create(cfg, host_weights, n_weights, device));
+  });
+}
+
+int agpt_vae_decode(agpt_handle h, const float* z, int B, int H, int W, float* out, void* stream) {
+  return guarded([&] {
+    AGPT_CHECK(z && out, "null argument");
+    vae_decode(as(h, kMagicVae, "vae"), z, B, H, W, out, (cudaStream_t)stream);
+  });
+}
+
 int agpt_bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, int epi_res, int use_tc, int reps,
                        int check, double* out3, double* dbg8_or_null) {
   return guarded([&] { bench_tapconv(G, L, Cin, Cout, K, dil, Wreal, epi_res, use_tc, reps, check, out3, dbg8_or_null); });

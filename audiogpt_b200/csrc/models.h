@@ -34,6 +34,9 @@ void unet_ddim_sample(Handle* h, const float* x_T, int B, int H, int W, int S, c
                       float cfg_scale, float* x_out, float* pred_x0_out, cudaStream_t st);
 long unet_launches_per_step(Handle* h);
 
+Handle* vae_create(const agpt_vae_cfg* cfg, const float* const* W, int nW, int device);
+void vae_decode(Handle* h, const float* z, int B, int H, int W, float* out, cudaStream_t st);
+
 void bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, int epi_res, int use_tc, int reps,
                    int check, double* out, double* dbg_avg, double x_scale = 1.0, double w_spread = 1.0, double* rel2 = nullptr);
 

@@ -243,6 +243,79 @@ void attention(const float* q, int q_pitch, const float* k, int k_pitch, const f
   AGPT_CUDA(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------ single-head attention with a wide head (VAE AttnBlock)
+// softmax_j(q_i . k_j * C^-0.5) v_j with d = C = 256 / 512 and 780 / 3 120 tokens (ldm/modules/diffusionmodules/
+// model.py:177-203) runs as two tap-GEMMs with an ACTIVATION as the weight operand (K^T, then V) and a row softmax
+// in between; these helpers build the operand layouts the tap-GEMM expects ([cin_pad][cout_pad], zero padded).
+__global__ void transpose_pad_kernel(const float* __restrict__ in, int in_pitch, int rows, int cols,
+                                     float* __restrict__ out, int rows_pad) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(long)r * in_pitch + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows_pad) out[(long)c * rows_pad + r] = tile[threadIdx.x][i];
+  }
+}
+// out [cols][rows_pad] = in[rows][cols]^T, columns rows..rows_pad-1 zero
+void transpose_pad(const float* in, int in_pitch, int rows, int cols, float* out, int rows_pad, cudaStream_t st) {
+  dim3 grid(cdiv(rows_pad, 32), cdiv(cols, 32)), block(32, 8);
+  transpose_pad_kernel<<<grid, block, 0, st>>>(in, in_pitch, rows, cols, out, rows_pad);
+  count_launch(1);
+  AGPT_CUDA(cudaGetLastError());
+}
+__global__ void copy_pad_rows_kernel(const float* __restrict__ in, int in_pitch, int rows, int cols,
+                                     float* __restrict__ out, long total) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / cols;
+    const int c = (int)(i - r * cols);
+    out[i] = r < rows ? in[r * in_pitch + c] : 0.f;
+  }
+}
+// out [rows_pad][cols] = in[rows][cols], rows beyond `rows` zero
+void copy_pad_rows(const float* in, int in_pitch, int rows, int cols, float* out, int rows_pad, cudaStream_t st) {
+  const long total = (long)rows_pad * cols;
+  copy_pad_rows_kernel<<<(unsigned)std::min<long>(cdivl(total, 256), 4096), 256, 0, st>>>(in, in_pitch, rows, cols, out, total);
+  count_launch(1);
+  AGPT_CUDA(cudaGetLastError());
+}
+// in-place softmax over the first `cols` entries of every row of x [rows][pitch], after scaling by `scale`
+// (torch: softmax(w_ * c^-0.5, dim=2)); entries cols..pitch-1 are set to zero.  One 256-thread block per row.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, int pitch, int cols, float scale) {
+  __shared__ float red[8];
+  float* xr = x + (long)blockIdx.x * pitch;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += 256) m = fmaxf(m, xr[c] * scale);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float s = 0.f;
+  for (int c = threadIdx.x; c < cols; c += 256) { const float e = expf(xr[c] * scale - m); xr[c] = e; s += e; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += red[i];
+  const float inv = 1.f / s;
+  for (int c = threadIdx.x; c < pitch; c += 256) xr[c] = c < cols ? xr[c] * inv : 0.f;
+}
+void softmax_rows(float* x, int pitch, long rows, int cols, float scale, cudaStream_t st) {
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(x, pitch, cols, scale);
+  count_launch(1);
+  AGPT_CUDA(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------ timestep embedding (cos || sin)
 struct TParam { int t[256]; };
 __global__ void timestep_embed_kernel(float* __restrict__ out, const __grid_constant__ TParam tp, int dim) {

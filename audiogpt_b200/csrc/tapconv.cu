@@ -105,22 +105,13 @@ tapconv_kernel(const __grid_constant__ TapConvParams P) {
   float* Ws = Xs + 4 * KC * R;
 
   const int tid = threadIdx.x, tx = tid % NTX, ty = tid / NTX;
-  const int g = blockIdx.z, co0 = blockIdx.y * BN, q0 = blockIdx.x * BM;
-  const int Wv = P.Wreal > 0 ? P.Wreal + 1 : 0;
-  const int Lv = Wv ? (P.L / P.Wreal) * Wv : P.L;
+  const int gz = blockIdx.z, g = tc_sample(P, gz), co0 = blockIdx.y * BN, q0 = blockIdx.x * BM;
+  const int Wv = tc_wv(P);
+  const int Lv = tc_lv(P);
 
   for (int i = tid; i < R + 8; i += NT) {
-    const int q = q0 + P.lo_al + i;
-    int a = -1;
-    if (q >= 0 && q < Lv) {
-      if (Wv) {
-        const int h = q / Wv, w = q - h * Wv;
-        if (w < P.Wreal) a = (h * P.Wreal + w) * P.in_pitch;
-      } else {
-        a = q * P.in_pitch;
-      }
-    }
-    rowaddr[i] = a;
+    const int r = tc_row_in(P, gz, q0 + P.lo_al + i, Wv, Lv);
+    rowaddr[i] = r >= 0 ? r * P.in_pitch : -1;
   }
 
   const float* __restrict__ ing = P.in + g * P.in_gstride;
@@ -203,14 +194,8 @@ tapconv_kernel(const __grid_constant__ TapConvParams P) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + (i - 4));
-    const int q = q0 + r;
-    if (q >= Lv) continue;
-    int p = q;
-    if (Wv) {
-      const int h = q / Wv, w = q - h * Wv;
-      if (w >= P.Wreal) continue;
-      p = h * P.Wreal + w;
-    }
+    const int p = tc_row_out(P, gz, q0 + r, Wv, Lv);
+    if (p < 0) continue;
     tc_epilogue(P, g, p, co0 + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
     tc_epilogue(P, g, p, co0 + BN / 2 + tx * 4, make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
   }
@@ -225,11 +210,10 @@ static void fma_launch(TapConvParams P, cudaStream_t st) {
   int R = round_up(TC_BM + (hi - P.lo_al), 4);
   while (R % 32 != 4) R += 4;
   P.R = R;
-  const int Wv = P.Wreal > 0 ? P.Wreal + 1 : 0;
-  const int Lv = Wv ? (P.L / P.Wreal) * Wv : P.L;
+  const int Lv = tc_lv(P);
   const int bn = tc_pick_bn(P.Cout);
   const size_t smem = ((size_t)(R + 8) + 4 * TC_KC * (size_t)R + 2 * TC_KC * (size_t)bn) * sizeof(float);
-  dim3 grid(cdiv(Lv, TC_BM), cdiv(P.Cout, bn), P.G);
+  dim3 grid(cdiv(Lv, TC_BM), cdiv(P.Cout, bn), tc_groups(P));
   int dev = 0;
   AGPT_CUDA(cudaGetDevice(&dev));
   static bool attr_done_dev[64] = {false};

@@ -58,7 +58,40 @@ struct TapConvParams {
   int tc_bn, tc_na, tc_nw, tc_nr, tc_nwk, tc_nb, tc_tps, tc_flags, tc_flags_user;   // tc_bn == 0 => FMA only
   long long* dbg;      // optional per-CTA phase timestamps (tc_flags & 2)
   float flops_scale;   // useful fraction of the MACs (zero-padded polyphase taps); 0 => 1
+  // 2-D convs on WIDE images (the VAE decoder's 80x624 maps): the image is cut into `strips` vertical strips of
+  // `strip_w` columns; grid slice gz = g * strips + s works on the virtual grid [H][strip_w + 2] of strip s
+  // (column j <-> image column s*strip_w + j - 1: one halo column on each side, zero outside the image), so
+  // the halo of a 128-row tile stays 2*(strip_w+2)+2 rows whatever the image width is.  strips == 0: one virtual
+  // grid [H][W + 1] per sample (one shared zero column), as the UNet's 10x78 maps use.
+  int strips, strip_w;
 };
+
+__host__ __device__ inline int tc_wv(const TapConvParams& P) { return P.Wreal > 0 ? (P.strips > 0 ? P.strip_w + 2 : P.Wreal + 1) : 0; }
+__host__ __device__ inline int tc_lv(const TapConvParams& P) { const int wv = tc_wv(P); return wv ? (P.L / P.Wreal) * wv : P.L; }
+__host__ __device__ inline int tc_groups(const TapConvParams& P) { return P.strips > 0 ? P.G * P.strips : P.G; }
+__host__ __device__ inline int tc_sample(const TapConvParams& P, int gz) { return P.strips > 0 ? gz / P.strips : gz; }
+// virtual row q of grid slice gz -> row index inside the sample's [L][C] tensor, or -1 (zero padding / no output)
+__host__ __device__ inline int tc_row_in(const TapConvParams& P, int gz, int q, int Wv, int Lv) {
+  if (q < 0 || q >= Lv) return -1;
+  if (!Wv) return q;
+  const int h = q / Wv, j = q - h * Wv;
+  if (P.strips > 0) {
+    const int w = (gz % P.strips) * P.strip_w + j - 1;
+    return (w >= 0 && w < P.Wreal) ? h * P.Wreal + w : -1;
+  }
+  return j < P.Wreal ? h * P.Wreal + j : -1;
+}
+__host__ __device__ inline int tc_row_out(const TapConvParams& P, int gz, int q, int Wv, int Lv) {
+  if (q < 0 || q >= Lv) return -1;
+  if (!Wv) return q;
+  const int h = q / Wv, j = q - h * Wv;
+  if (P.strips > 0) {
+    if (j < 1 || j > P.strip_w) return -1;
+    const int w = (gz % P.strips) * P.strip_w + j - 1;
+    return w < P.Wreal ? h * P.Wreal + w : -1;
+  }
+  return j < P.Wreal ? h * P.Wreal + j : -1;
+}
 
 // ---------------------------------------------------------------- host side
 struct PackedConv {
@@ -121,6 +154,16 @@ inline TapConvParams tapconv_params(const PackedConv& pc, int G, int L, int Wrea
   P.tc_bn = pc.tc_bn;
   P.w_h = pc.w_h.p; P.w_h256 = pc.w_h256.p; P.w_h64 = pc.w_h64.p; P.tc_chunks_h = pc.h_chunks; P.tc_descale = pc.h_descale;
   return P;
+}
+
+// Switch a 3x3 launch to strip mode (see TapConvParams::strips): strips of at most `strip_w` columns.
+inline void tapconv_set_strips(TapConvParams& P, int strip_w) {
+  AGPT_CHECK(P.Wreal > 0 && P.ntaps == 9 && strip_w >= 8, "strip mode is for 3x3 convs");
+  P.strips = cdiv(P.Wreal, strip_w);
+  P.strip_w = strip_w;
+  const int Wv = strip_w + 2;
+  for (int dh = -1, t = 0; dh <= 1; ++dh)
+    for (int dw = -1; dw <= 1; ++dw, ++t) P.tap_off[t] = dh * Wv + dw;
 }
 
 // ---- host-side weight packing (reference layouts -> [tap][cin_pad][cout_pad]) ----

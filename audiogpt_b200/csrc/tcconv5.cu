@@ -72,9 +72,9 @@ __global__ void __launch_bounds__(NWK == 256 ? V5_THREADS : 192, 1) tcconv5_kern
   const int xt = warp < 4 ? tid : tid - 64;      // worker thread index 0..NWK-1
   const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
   const int sub = warp < 4 ? 0 : 1;               // which of the two worker warps of that quadrant
-  const int g = blockIdx.z, co0 = blockIdx.y * BN, q0 = blockIdx.x * TC_ROWS;
-  const int Wv = P.Wreal > 0 ? P.Wreal + 1 : 0;
-  const int Lv = Wv ? (P.L / P.Wreal) * Wv : P.L;
+  const int gz = blockIdx.z, g = tc_sample(P, gz), co0 = blockIdx.y * BN, q0 = blockIdx.x * TC_ROWS;
+  const int Wv = tc_wv(P);
+  const int Lv = tc_lv(P);
   const int nchunks = P.tc_chunks_h, ntaps = P.ntaps, total = nchunks * ntaps;
   const int lo = P.lo_al;
   const bool dbg_on = (P.tc_flags & 2) && P.dbg;
@@ -94,31 +94,10 @@ __global__ void __launch_bounds__(NWK == 256 ? V5_THREADS : 192, 1) tcconv5_kern
   }
   if (is_worker) {
     for (int i = xt; i < RRA; i += NWK) {
-      const int q = q0 + lo + i;
-      int a = -1;
-      if (q >= 0 && q < Lv) {
-        if (Wv) {
-          const int h = q / Wv, w = q - h * Wv;
-          if (w < P.Wreal) a = (h * P.Wreal + w) * P.in_pitch;
-        } else {
-          a = q * P.in_pitch;
-        }
-      }
-      rowinfo[i] = a;
+      const int r = tc_row_in(P, gz, q0 + lo + i, Wv, Lv);
+      rowinfo[i] = r >= 0 ? r * P.in_pitch : -1;
     }
-    if (xt < TC_ROWS) {  // output row -> real position (or -1)
-      const int q = q0 + xt;
-      int p = -1;
-      if (q < Lv) {
-        if (Wv) {
-          const int h = q / Wv, w = q - h * Wv;
-          if (w < P.Wreal) p = h * P.Wreal + w;
-        } else {
-          p = q;
-        }
-      }
-      rowp[xt] = p;
-    }
+    if (xt < TC_ROWS) rowp[xt] = tc_row_out(P, gz, q0 + xt, Wv, Lv);   // output row -> real position (or -1)
   }
   tc_fence_before();
   __syncthreads();
@@ -416,9 +395,8 @@ static bool tcconv5_try(TapConvParams P, int BN, cudaStream_t st) {
   tc5_layout(S, BN, RRA, NA, NW, NR);
   const size_t smem = (size_t)S.total + 1024;
   if (smem > (size_t)kMaxDyn) return false;
-  const int Wv = P.Wreal > 0 ? P.Wreal + 1 : 0;
-  const int Lv = Wv ? (P.L / P.Wreal) * Wv : P.L;
-  dim3 grid(cdiv(Lv, TC_ROWS), cdiv(P.Cout, BN), P.G);
+  const int Lv = tc_lv(P);
+  dim3 grid(cdiv(Lv, TC_ROWS), cdiv(P.Cout, BN), tc_groups(P));
   int dev = 0;
   AGPT_CUDA(cudaGetDevice(&dev));
   static bool attr_done_dev[64] = {false};
@@ -444,9 +422,8 @@ static bool tcconv5_try(TapConvParams P, int BN, cudaStream_t st) {
 HTile pick_h_tile(const TapConvParams& P, int sms) {
   static int allow256 = -1;
   if (allow256 < 0) { const char* e = getenv("AGPT_TC_BN256"); allow256 = (e && e[0] == '0') ? 0 : 1; }
-  const int Wv = P.Wreal > 0 ? P.Wreal + 1 : 0;
-  const int Lv = Wv ? (P.L / P.Wreal) * Wv : P.L;
-  const long rt = (long)cdiv(Lv, TC_ROWS) * P.G;
+  const int Lv = tc_lv(P);
+  const long rt = (long)cdiv(Lv, TC_ROWS) * tc_groups(P);
   auto cost = [](int bn) { return bn == 256 ? 1.7 : (bn == 128 ? 1.0 : (bn == 64 ? 0.62 : 0.45)); };
   HTile best{P.tc_bn, P.w_h, rt * cdiv(P.Cout, P.tc_bn)};
   double bs = (double)cdiv(best.ntiles, (long)sms) * cost(P.tc_bn);

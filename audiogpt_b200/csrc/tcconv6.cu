@@ -680,7 +680,7 @@ static bool tcconv6_try(TapConvParams P, int BN, cudaStream_t st) {
 // Persistent schedule: pays when a CTA gets more than one tile (otherwise there is nothing to overlap
 // and v5's 8 transform+epilogue warps are at least as good).  Returns false -> caller uses v5.
 bool tcconv6_launch(TapConvParams P, cudaStream_t st, bool force) {
-  if (!P.w_h) return false;
+  if (!P.w_h || P.strips > 0) return false;     // strip-tiled wide images run on tcconv5
   int dev = 0;
   AGPT_CUDA(cudaGetDevice(&dev));
   static int sms_dev[64] = {0};

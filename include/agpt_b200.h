@@ -195,6 +195,26 @@ int agpt_unet_ddim_sample(agpt_handle h, const float* x_T, int B, int H, int W, 
 /* kernels launched per DDIM step by the last agpt_unet_ddim_sample call (bench.py reports it) */
 long agpt_unet_launches_per_step(agpt_handle h);
 
+/* ------------------------------------------------------------------ AutoencoderKL.decode (first stage)
+ * Replaces AutoencoderKL.decode = post_quant_conv -> Decoder.forward
+ * (text_to_audio/Make_An_Audio/ldm/models/autoencoder.py:351-354,
+ *  ldm/modules/diffusionmodules/model.py:462-568; ResnetBlock :121-143, AttnBlock :150-203, Upsample :43-49):
+ * the step between DDIMSampler.sample and the vocoder on every text-to-audio call
+ * (ddpm.py decode_first_stage; audio-chatgpt.py:174).                                                  */
+typedef struct {
+  int embed_dim, z_channels;            /* 4, 4 */
+  int ch, out_ch;                       /* 128, 1 */
+  int num_levels;                       /* len(ch_mult) */
+  int ch_mult[AGPT_MAX_LEVELS];
+  int num_res_blocks;                   /* the decoder uses num_res_blocks + 1 blocks per level */
+  int attn_at_level[AGPT_MAX_LEVELS];   /* 1 if resolution / 2^level is in attn_resolutions (model.py:481,517) */
+} agpt_vae_cfg;
+/* host_weights: fp32 HOST arrays in the key order of audiogpt_b200.specs.vae_decoder_param_shapes(cfg). */
+int agpt_vae_create(const agpt_vae_cfg* cfg, const float* const* host_weights, int n_weights, int device,
+                    agpt_handle* out);
+/* z [B, embed_dim, H, W] (device) -> out [B, out_ch, H * 2^(levels-1), W * 2^(levels-1)] (device) */
+int agpt_vae_decode(agpt_handle h, const float* z, int B, int H, int W, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
