@@ -93,6 +93,16 @@ int agpt_hifigan_vocode_host(agpt_handle h, const float* mel_host, const float* 
   });
 }
 
+int agpt_nsf_source(const float* f0, int B, int L, int dim, float sampling_rate, const float* lin_w_host, float lin_b,
+                    const float* rand_ini_or_null, const float* noise_or_null, float sine_amp, float noise_std,
+                    float voiced_threshold, float* har_source, void* stream) {
+  return guarded([&] {
+    AGPT_CHECK(f0 && lin_w_host && har_source, "null argument");
+    nsf_source(f0, B, L, dim, sampling_rate, lin_w_host, lin_b, rand_ini_or_null, noise_or_null, sine_amp, noise_std,
+               voiced_threshold, har_source, (cudaStream_t)stream);
+  });
+}
+
 int agpt_diffnet_create(const agpt_diffnet_cfg* cfg, const float* const* host_weights, int n_weights, int device,
                         agpt_handle* out) {
   return guarded([&] {

@@ -184,6 +184,128 @@ __global__ void nsf_add_kernel(float* __restrict__ x, const float* __restrict__ 
   x[((long)b * L + p) * C + c] += acc;
 }
 
+// ------------------------------------------------------------------ NSF harmonic source (SourceModuleHnNSF)
+// NeuralSeq/modules/parallel_wavegan/models/source.py:311-441 (SineGen), :484-532 (SourceModuleHnNSF):
+//   rad[t,h]  = (f0[t] * (h+1) / sr) mod 1          (+ rand_ini[h] at t = 0, rand_ini[0] = 0)
+//   sines     = sin(2 pi * cumsum_t(rad)) * sine_amp   -- the reference subtracts 1 whenever the running sum wraps
+//                                                         (source.py:369-377); sin is 1-periodic in that sum, so the
+//                                                         phase is the FRACTIONAL part of the prefix sum
+//   x[t,h]    = sines * uv[t] + (uv * noise_std + (1 - uv) * sine_amp / 3) * noise[t,h],   uv = f0 > threshold
+//   har[t]    = tanh(b + sum_h w[h] * x[t,h])
+// The prefix sum over the 10^5 samples of an utterance is a three-level scan in double precision (chunk sums ->
+// one sequential pass over the chunk sums per (utterance, harmonic) -> in-chunk block scan), so the phase is exact to
+// fp64 rounding where the reference's sequential fp32 cumsum drifts by ~1e-5 cycles; the random draws (initial
+// phases, noise) stay with the caller in the reference's torch call order.
+constexpr int NSF_CHUNK = 1024, NSF_MAXH = 16;
+struct NsfLin { float w[NSF_MAXH]; float b; };
+
+__device__ __forceinline__ float nsf_rad(float f0, int h, float sr) {
+  const float v = (f0 * (float)(h + 1)) / sr;      // f0_buf[:, :, h] = f0 * (h + 1); (f0_values / sampling_rate) % 1
+  return v - floorf(v);                             // torch's % on floats: result in [0, 1)
+}
+
+// chunk sums: grid (nchunks, dim, B)
+__global__ void nsf_chunk_sum_kernel(const float* __restrict__ f0, double* __restrict__ csum, int L, int dim, float sr) {
+  __shared__ double red[8];
+  const int c = blockIdx.x, h = blockIdx.y, b = blockIdx.z, nch = gridDim.x;
+  const float* fb = f0 + (long)b * L;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < NSF_CHUNK; i += blockDim.x) {
+    const int t = c * NSF_CHUNK + i;
+    if (t < L) s += (double)nsf_rad(fb[t], h, sr);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    csum[((long)b * dim + h) * nch + c] = t;
+  }
+}
+// exclusive scan of the chunk sums (fractional part), seeded with the initial phase: one thread per (b, h)
+__global__ void nsf_chunk_scan_kernel(double* __restrict__ csum, const float* __restrict__ rand_ini, int nch, int dim, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * dim) return;
+  const int h = i % dim;
+  double acc = (h == 0 || !rand_ini) ? 0.0 : (double)rand_ini[i];
+  double* cs = csum + (long)i * nch;
+  for (int c = 0; c < nch; ++c) {
+    const double v = cs[c];
+    cs[c] = acc;
+    acc += v;
+    acc -= floor(acc);
+  }
+}
+// in-chunk inclusive scan + sines + merge: grid (nchunks, B), 256 threads x 4 samples
+__global__ void __launch_bounds__(256) nsf_source_kernel(const float* __restrict__ f0, const double* __restrict__ cbase,
+                                                          const float* __restrict__ noise, float* __restrict__ har,
+                                                          int L, int dim, float sr, float sine_amp, float noise_std, float thr,
+                                                          NsfLin lin) {
+  __shared__ double wsum[8];
+  const int c = blockIdx.x, b = blockIdx.y, nch = gridDim.x;
+  const int t0 = c * NSF_CHUNK + threadIdx.x * 4;
+  const float* fb = f0 + (long)b * L;
+  float fv[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) fv[k] = (t0 + k < L) ? fb[t0 + k] : 0.f;
+  float acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] = lin.b;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int h = 0; h < dim; ++h) {
+    double r[4], run = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { run += (double)nsf_rad(fv[k], h, sr); r[k] = run; }     // thread-local inclusive sums
+    double inc = run;                                                                       // warp inclusive scan of the thread totals
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    __syncthreads();
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    double base = cbase[((long)b * dim + h) * nch + c];
+    for (int w = 0; w < warp; ++w) base += wsum[w];
+    base += inc - run;                                                                      // exclusive prefix of this thread
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int t = t0 + k;
+      if (t >= L) continue;
+      double ph = base + r[k];
+      ph -= floor(ph);
+      const float sn = sinf((float)ph * 6.283185307179586f) * sine_amp;
+      const float uv = fv[k] > thr ? 1.f : 0.f;
+      const float na = uv * noise_std + (1.f - uv) * sine_amp / 3.f;
+      const float nz = noise ? noise[((long)b * L + t) * dim + h] : 0.f;
+      acc[k] = fmaf(lin.w[h], sn * uv + na * nz, acc[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (t0 + k < L) har[(long)b * L + t0 + k] = tanhf(acc[k]);
+}
+
+static DevBuf g_nsf_scratch[16];
+
+// f0 [B][L] (already at the sample rate), rand_ini [B][dim] or null, noise [B][L][dim] or null -> har [B][L]
+void nsf_source(const float* f0, int B, int L, int dim, float sr, const float* lin_w_host, float lin_b,
+                const float* rand_ini, const float* noise, float sine_amp, float noise_std, float thr, float* har,
+                cudaStream_t st) {
+  AGPT_CHECK(B >= 1 && L >= 1 && dim >= 1 && dim <= NSF_MAXH, "nsf_source: bad shape (at most 16 harmonics)");
+  int dev = 0;
+  AGPT_CUDA(cudaGetDevice(&dev));
+  const int nch = cdiv(L, NSF_CHUNK);
+  double* cs = reinterpret_cast<double*>(g_nsf_scratch[dev & 15].ensure((size_t)B * dim * nch * 2 + 2));
+  NsfLin lin;
+  for (int h = 0; h < NSF_MAXH; ++h) lin.w[h] = h < dim ? lin_w_host[h] : 0.f;
+  lin.b = lin_b;
+  nsf_chunk_sum_kernel<<<dim3(nch, dim, B), 256, 0, st>>>(f0, cs, L, dim, sr);
+  nsf_chunk_scan_kernel<<<cdiv(B * dim, 64), 64, 0, st>>>(cs, rand_ini, nch, dim, B);
+  nsf_source_kernel<<<dim3(nch, B), 256, 0, st>>>(f0, cs, noise, har, L, dim, sr, sine_amp, noise_std, thr, lin);
+  count_launch(3);
+  AGPT_CUDA(cudaGetLastError());
+}
+
 struct SnakeW { DevBuf a, inv_b; };   // per-channel exp(alpha) (or alpha) and 1 / (beta + 1e-9)
 
 struct ResBlockW {

@@ -15,6 +15,10 @@ Handle* hifigan_create(const agpt_hifigan_cfg* cfg, const float* const* W, int n
 void hifigan_forward(Handle* h, const float* mel, const float* har, int B, int T, float* wav, cudaStream_t st);
 void hifigan_vocode_host(Handle* h, const float* mel_host, const float* har_host, int B, int T, float* wav_host);
 
+void nsf_source(const float* f0, int B, int L, int dim, float sr, const float* lin_w_host, float lin_b,
+                const float* rand_ini, const float* noise, float sine_amp, float noise_std, float thr, float* har,
+                cudaStream_t st);
+
 Handle* diffnet_create(const agpt_diffnet_cfg* cfg, const float* const* W, int nW, int device);
 void diffnet_set_cond(Handle* h, const float* cond, int B, int T, cudaStream_t st);
 void diffnet_eps(Handle* h, const float* x, const int* t_host, float* eps, cudaStream_t st);

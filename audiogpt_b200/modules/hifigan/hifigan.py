@@ -47,37 +47,58 @@ def fold_weight_norm(g: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
 
 
 class SourceModuleHnNSF(nn.Module):
-    """Harmonic-plus-noise excitation (host-side PyTorch ops; same RNG call order as
-    NeuralSeq/modules/parallel_wavegan/models/source.py:311-441,484-532 so that a seeded
-    run draws the same numbers).  Negligible FLOPs; SURVEY.md 8(f)-3 'next' row."""
+    """Harmonic-plus-noise excitation, drop-in for ``SourceModuleHnNSF`` + ``SineGen``
+    (NeuralSeq/modules/parallel_wavegan/models/source.py:311-441,484-532): same constructor, same
+    ``forward(f0 [B, L, 1]) -> (sine_merge [B, L, 1], noise [B, L, 1], uv [B, L, 1])``, same ``l_linear.*`` keys.
 
-    def __init__(self, sampling_rate, harmonic_num=8, sine_amp=0.1, add_noise_std=0.003, voiced_threshold=0):
+    The arithmetic (phase prefix sum, 9 harmonic sines, uv gating, noise mix, Linear(9 -> 1) + tanh) is ONE fused
+    pass in libagpt_b200.so (agpt_nsf_source: a three-level fp64 scan over the ~10^5 samples of an utterance); the
+    random draws stay in torch, in the reference's call order and shapes -- ``torch.rand(B, dim)`` (initial
+    phases), ``torch.randn_like(sines)``, ``torch.randn_like(uv)`` -- so a seeded run consumes the generator exactly
+    like the reference does.  CUDA only."""
+
+    def __init__(self, sampling_rate, harmonic_num=0, sine_amp=0.1, add_noise_std=0.003, voiced_threshod=0,
+                 voiced_threshold=None):
         super().__init__()
         self.sampling_rate, self.harmonic_num = sampling_rate, harmonic_num
-        self.sine_amp, self.noise_std, self.voiced_threshold = sine_amp, add_noise_std, voiced_threshold
+        self.sine_amp, self.noise_std = sine_amp, add_noise_std
+        self.voiced_threshold = voiced_threshod if voiced_threshold is None else voiced_threshold
         self.l_linear = nn.Linear(harmonic_num + 1, 1)
 
-    @torch.no_grad()
-    def forward(self, f0):  # f0 [B, L, 1]
+    def draw(self, f0):
+        """The three RNG draws of the reference, in its order: (rand_ini [B, dim], noise [B, L, dim], noise_src)."""
+        B, L, _ = f0.shape
         dim = self.harmonic_num + 1
-        mult = torch.arange(1, dim + 1, device=f0.device, dtype=f0.dtype)
-        f0_buf = f0 * mult[None, None, :]
-        rad = (f0_buf / self.sampling_rate) % 1
-        rand_ini = torch.rand(f0_buf.shape[0], f0_buf.shape[2], device=f0.device)
-        rand_ini[:, 0] = 0
-        rad[:, 0, :] = rad[:, 0, :] + rand_ini
-        wrapped = torch.cumsum(rad, 1) % 1
-        over = (wrapped[:, 1:, :] - wrapped[:, :-1, :]) < 0
-        shift = torch.zeros_like(rad)
-        shift[:, 1:, :] = over * -1.0
-        sines = torch.sin(torch.cumsum(rad + shift, dim=1) * 2 * np.pi) * self.sine_amp
+        rand_ini = torch.rand(B, dim, device=f0.device)
+        noise = torch.randn(B, L, dim, device=f0.device, dtype=f0.dtype)
+        noise_src = torch.randn(B, L, 1, device=f0.device, dtype=f0.dtype) * self.sine_amp / 3
+        return rand_ini, noise, noise_src
+
+    @torch.no_grad()
+    def forward(self, f0, rand_ini=None, noise=None):  # f0 [B, L, 1]
+        if not f0.is_cuda:
+            raise RuntimeError("audiogpt_b200.SourceModuleHnNSF runs on CUDA only (no CPU fallback)")
+        B, L, _ = f0.shape
+        dim = self.harmonic_num + 1
+        noise_src = None
+        if rand_ini is None or noise is None:
+            rand_ini, noise, noise_src = self.draw(f0)
+        if noise_src is None:
+            noise_src = torch.randn(B, L, 1, device=f0.device, dtype=f0.dtype) * self.sine_amp / 3
+        f0c = f0.reshape(B, L).contiguous().float()
+        w = self.l_linear.weight.detach().reshape(-1).float().cpu().numpy().copy()
+        b = float(self.l_linear.bias.detach().float().cpu()[0])
+        har = torch.empty((B, L), device=f0.device, dtype=torch.float32)
+        ri = rand_ini.contiguous().float()
+        nz = noise.contiguous().float()
+        with torch.cuda.device(f0.device):
+            _lib.check(_lib.lib().agpt_nsf_source(
+                _lib.fptr(f0c), B, L, dim, C.c_float(float(self.sampling_rate)), w.ctypes.data_as(C.c_void_p),
+                C.c_float(b), _lib.fptr(ri), _lib.fptr(nz), C.c_float(float(self.sine_amp)),
+                C.c_float(float(self.noise_std)), C.c_float(float(self.voiced_threshold)), _lib.fptr(har),
+                _lib.cur_stream(f0.device)))
         uv = (f0 > self.voiced_threshold).to(f0.dtype)
-        noise_amp = uv * self.noise_std + (1 - uv) * self.sine_amp / 3
-        noise = noise_amp * torch.randn_like(sines)
-        sines = sines * uv + noise
-        merged = torch.tanh(self.l_linear(sines))
-        noise_src = torch.randn_like(uv) * self.sine_amp / 3
-        return merged, noise_src, uv
+        return har[:, :, None], noise_src, uv
 
 
 class HifiGanGenerator(nn.Module, _lib.HandleOwner):
@@ -157,7 +178,8 @@ class HifiGanGenerator(nn.Module, _lib.HandleOwner):
     def _cfg(self):
         h = self.h
         c = _lib.HifiganCfg()
-        c.n_mels, c.c_out = 80, self.c_out
+        # the reference hard-codes Conv1d(80, ...) for conv_pre (hifigan.py:118); take it from the parameter table
+        c.n_mels, c.c_out = int(self._shapes["conv_pre.weight"][1]), self.c_out
         c.upsample_initial_channel = int(h["upsample_initial_channel"])
         c.num_upsamples = self.num_upsamples
         for i, (u, k) in enumerate(zip(h["upsample_rates"], h["upsample_kernel_sizes"])):

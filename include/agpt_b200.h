@@ -103,6 +103,17 @@ int agpt_hifigan_forward(agpt_handle h, const float* mel, const float* har_sourc
 int agpt_hifigan_vocode_host(agpt_handle h, const float* mel_host, const float* har_host,
                              int B, int T, float* wav_host);
 
+/* NSF harmonic source: replaces SineGen.forward + SourceModuleHnNSF.forward
+ * (NeuralSeq/modules/parallel_wavegan/models/source.py:311-441,484-532; call site hifigan.py:145-149).
+ * f0 [B][L] device, ALREADY upsampled to the sample rate (hifigan.py:147 f0_upsamp); dim = harmonic_num + 1 (<= 16);
+ * lin_w_host [dim], lin_b: m_source.l_linear; rand_ini [B][dim] (torch.rand, entry 0 ignored) and noise [B][L][dim]
+ * (torch.randn_like(sines)) are drawn by the caller in the reference's order, NULL = zeros.
+ * har_source [B][L] = tanh(l_linear(sines * uv + noise_amp * noise)): the array agpt_hifigan_forward takes.
+ * The phase prefix sum over the whole utterance is a three-level scan in fp64.                            */
+int agpt_nsf_source(const float* f0, int B, int L, int dim, float sampling_rate, const float* lin_w_host, float lin_b,
+                    const float* rand_ini_or_null, const float* noise_or_null, float sine_amp, float noise_std,
+                    float voiced_threshold, float* har_source, void* stream);
+
 /* ------------------------------------------------------------------ DiffNet + GaussianDiffusion
  * Replaces DiffNet.forward (NeuralSeq/modules/diff/net.py:107-130) and the
  * elementwise part of GaussianDiffusion.p_sample / p_sample_plms

@@ -102,6 +102,33 @@ def hifigan_forward(sd, h, mel, har_source=None):
         return torch.tanh(x)
 
 
+def nsf_source(lin_w, lin_b, f0_up, sampling_rate, rand_ini, noise, harmonic_num=8, sine_amp=0.1, noise_std=0.003,
+               voiced_threshold=0.0):
+    """SineGen.forward + SourceModuleHnNSF.forward (NeuralSeq/modules/parallel_wavegan/models/source.py:346-441,
+    517-526) with the three random draws made explicit: f0_up [B, L, 1] (already at the sample rate), rand_ini
+    [B, dim] (torch.rand; column 0 is zeroed like :357), noise [B, L, dim] (torch.randn_like(sines)).
+    Returns sine_merge [B, L, 1]."""
+    import numpy as np
+    dim = harmonic_num + 1
+    f0_buf = torch.zeros(f0_up.shape[0], f0_up.shape[1], dim)
+    f0_buf[:, :, 0] = f0_up[:, :, 0]
+    for idx in range(harmonic_num):
+        f0_buf[:, :, idx + 1] = f0_buf[:, :, 0] * (idx + 2)
+    rad = (f0_buf / sampling_rate) % 1
+    ri = rand_ini.clone()
+    ri[:, 0] = 0
+    rad[:, 0, :] = rad[:, 0, :] + ri
+    tmp = torch.cumsum(rad, 1) % 1
+    over = (tmp[:, 1:, :] - tmp[:, :-1, :]) < 0
+    shift = torch.zeros_like(rad)
+    shift[:, 1:, :] = over * -1.0
+    sines = torch.sin(torch.cumsum(rad + shift, dim=1) * 2 * np.pi) * sine_amp
+    uv = torch.ones_like(f0_up) * (f0_up > voiced_threshold)
+    noise_amp = uv * noise_std + (1 - uv) * sine_amp / 3
+    sines = sines * uv + noise_amp * noise
+    return torch.tanh(F.linear(sines, lin_w, lin_b))
+
+
 def hifigan_flops(h, T, c_out=1, n_mels=80):
     """2*MAC count of one forward at T frames (245.6 GFLOP at V1, T=400)."""
     c = int(h["upsample_initial_channel"])

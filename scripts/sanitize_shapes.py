@@ -1,0 +1,24 @@
+"""Run the 12 layer shapes of tests/test_pipeline_gpu.py::SHAPES through one tcgen05 schedule (argv[1]: 5 | 6 | 7) with
+and without a residual epilogue -- the workload for `compute-sanitizer --tool memcheck|racecheck|synccheck`
+(VERDICT r1 weak #11).  Prints one line per shape; exits non-zero on a parity failure."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from audiogpt_b200 import _lib
+SHAPES = [(2, 3000, 256, 256, 11, 5, 0), (2, 5000, 128, 128, 3, 3, 0), (2, 9000, 32, 32, 7, 1, 0),
+          (3, 400, 256, 512, 3, 2, 0), (1, 777, 320, 320, 1, 1, 0), (2, 780, 320, 320, 3, 1, 78),
+          (2, 195, 640, 640, 3, 1, 39), (1, 130, 1280, 320, 1, 1, 0), (2, 4, 64, 96, 3, 1, 0),
+          (2, 300, 80, 256, 7, 1, 0), (1, 780, 4, 320, 3, 1, 78), (2, 500, 96, 40, 5, 2, 0)]
+ver = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+L = _lib.lib()
+torch.zeros(1).cuda()
+_lib.check(L.agpt_set_tc_version(ver))
+bad = 0
+for G, Ln, Cin, Cout, K, dil, Wr in SHAPES:
+    for epi_res in (0, 1):
+        rel = (C.c_double * 2)()
+        _lib.check(L.agpt_check_tapconv(G, Ln, Cin, Cout, K, dil, Wr, epi_res, C.c_double(1.0), C.c_double(1.0), rel))
+        ok = rel[0] < 2e-5
+        bad += 0 if ok else 1
+        print(f"v{ver} G={G} L={Ln} {Cin}->{Cout} k={K} dil={dil} W={Wr} res={epi_res}: max/rms {rel[0]:.2e} rms/rms {rel[1]:.2e} {'ok' if ok else 'FAIL'}", flush=True)
+sys.exit(1 if bad else 0)

@@ -34,7 +34,13 @@ torch.manual_seed(0)
 torch.set_num_threads(os.cpu_count() or 1)
 
 
+_SAVE_ONLY = None   # set of fixture names to (re)write; None = all
+
+
 def save(name, **arrs):
+    if _SAVE_ONLY is not None and name not in _SAVE_ONLY:
+        print(f"(not rewriting {name}.npz)")
+        return
     out = {}
     for k, v in arrs.items():
         if torch.is_tensor(v):
@@ -62,8 +68,11 @@ def import_neuralseq():
     sys.path.insert(0, os.path.join(REF, "NeuralSeq"))
 
 
-def golden_hifigan():
+def golden_hifigan(nsf_only=False):
     from modules.hifigan.hifigan import HifiGanGenerator
+    global _SAVE_ONLY
+    if nsf_only:
+        _SAVE_ONLY = {"nsf_source"}
 
     # ---- small config, B=2, ragged-ish T=24 -----------------------------------------
     h = specs.HIFIGAN_SMALL
@@ -126,6 +135,34 @@ def golden_hifigan():
         wav3 = m4(mel3, f0)
     save("hifigan_small_nsf", mel=mel3, f0=f0, har_source=cap["har"].transpose(1, 2), wav=wav3)
 
+    # ---- the NSF source module itself with its random draws pinned --------------------------
+    # torch.rand / torch.randn_like are patched for the duration of the call: the reference then consumes
+    # exactly these tensors (rand_ini, randn_like(sines), randn_like(uv) -- in that order, source.py:356,433,523)
+    from unittest import mock
+    def nsf_case(B, T, seed):
+        f0f = 180.0 + 60.0 * specs.synth_tensor((B, T), seed=seed)          # frame-level F0 in Hz
+        f0f[:, : T // 8] = 0.0                                              # an unvoiced head
+        f0f[:, T // 2: T // 2 + max(1, T // 10)] = 0.0                      # and an unvoiced gap
+        f0u = torch.repeat_interleave(f0f[:, None], 256, dim=2).transpose(1, 2)      # nn.Upsample(scale_factor=hop), nearest
+        ri = torch.rand((B, 9), generator=torch.Generator().manual_seed(seed + 1))
+        nz = specs.synth_tensor((B, T * 256, 9), seed=seed + 2)
+        nz2 = specs.synth_tensor((B, T * 256, 1), seed=seed + 3)
+        draws = [nz, nz2]
+        with mock.patch.object(torch, "rand", lambda *a, **k: ri.clone()), \
+                mock.patch.object(torch, "randn_like", lambda x: draws.pop(0)):
+            with torch.no_grad():
+                har, noi, uv = m4.m_source(f0u)
+        assert not draws
+        return f0f, ri, har
+    f0a, ria, hara = nsf_case(2, 20, 150)
+    f0b, rib, harb = nsf_case(1, 400, 160)            # 102 400 samples: a 100-chunk prefix sum
+    print("nsf har rms", hara.pow(2).mean().sqrt().item(), harb.pow(2).mean().sqrt().item())
+    save("nsf_source", f0_a=f0a, rand_ini_a=ria, har_a=hara[:, :, 0], f0_b=f0b, rand_ini_b=rib,
+         har_b_head=harb[0, :8192, 0], har_b_stride=harb[0, ::53, 0], har_b_tail=harb[0, -4096:, 0])
+
+    if nsf_only:
+        _SAVE_ONLY = None
+        return
     # ---- V1 (BASELINE configs[0]: 1x80x400), subsampled -------------------------------
     hv = specs.HIFIGAN_V1
     sdv = specs.synth_hifigan(hv, 1234)
@@ -457,13 +494,15 @@ def golden_vae():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["hifigan", "diffusion", "c3", "ldm", "bigvgan", "vae"]   # extra selector: ldm100 (DDIM-100 end point only)
-    if "hifigan" in which or "diffusion" in which or "c3" in which:
+    if "nsf" in which:
+        which = list(which) + ["hifigan_nsf_only"]
+    if "hifigan" in which or "diffusion" in which or "c3" in which or "hifigan_nsf_only" in which:
         import_neuralseq()
         cwd = os.getcwd()
         os.chdir(os.path.join(REF, "NeuralSeq"))
         try:
-            if "hifigan" in which:
-                golden_hifigan()
+            if "hifigan" in which or "hifigan_nsf_only" in which:
+                golden_hifigan(nsf_only="hifigan" not in which)
             if "diffusion" in which:
                 golden_diffusion()
             if "c3" in which:

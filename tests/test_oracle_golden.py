@@ -7,7 +7,7 @@ from audiogpt_b200 import specs
 from oracle import diffusion_ref as dr
 from oracle import hifigan_ref as hr
 from oracle import ldm_ref as lr
-from conftest import load_golden, rel_rmse
+from conftest import load_golden, rel_rmse, rmse
 
 T = torch.tensor
 
@@ -62,6 +62,29 @@ def test_hifigan_v1_c1():
     assert rel_rmse(wav[0, 0, :4096], g["wav_head"]) < 2e-5
     assert rel_rmse(wav[0, 0, ::37], g["wav_stride"]) < 2e-5
     assert abs(hr.hifigan_flops(h, 400) / 245.64e9 - 1) < 0.01
+
+
+def _nsf_inputs(g, tag, B, Tn, seed):
+    f0f = T(g["f0_" + tag])
+    f0u = torch.repeat_interleave(f0f[:, None], 256, dim=2).transpose(1, 2)
+    nz = specs.synth_tensor((B, Tn * 256, 9), seed=seed + 2)
+    return f0u, T(g["rand_ini_" + tag]), nz
+
+
+def test_nsf_source_oracle_vs_reference():
+    """oracle.hifigan_ref.nsf_source == the reference's SourceModuleHnNSF with its random draws pinned
+    (fixture: make_golden.py nsf), short and 102 400-sample utterances."""
+    g = load_golden("nsf_source")
+    h3 = dict(specs.HIFIGAN_SMALL, use_pitch_embed=True, audio_sample_rate=24000)
+    sd = specs.synth_hifigan(h3, 5678)
+    w, b = sd["m_source.l_linear.weight"], sd["m_source.l_linear.bias"]
+    f0u, ri, nz = _nsf_inputs(g, "a", 2, 20, 150)
+    har = hr.nsf_source(w, b, f0u, 24000, ri, nz)
+    assert rmse(har[:, :, 0], g["har_a"]) < 1e-7
+    f0u, ri, nz = _nsf_inputs(g, "b", 1, 400, 160)
+    har = hr.nsf_source(w, b, f0u, 24000, ri, nz)[0, :, 0]
+    assert rmse(har[:8192], g["har_b_head"]) < 1e-7 and rmse(har[::53], g["har_b_stride"]) < 1e-7
+    assert rmse(har[-4096:], g["har_b_tail"]) < 1e-7
 
 
 def test_schedule_tables_bit_exact():
