@@ -50,6 +50,14 @@ int agpt_profile_collect(double ms[4], double flops[4], double bytes[4], long lo
   return guarded([&] { profile_collect(ms, flops, bytes, launches); });
 }
 int agpt_set_tensor_cores(int on) { return guarded([&] { tc_set_enabled(on); }); }
+int agpt_set_attention_tc(int on) { return guarded([&] { attention_set_tc(on); }); }
+int agpt_attention(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, float* o,
+                   int o_pitch, int N, int heads, int d, int Lq, int Lk, void* stream) {
+  return guarded([&] {
+    AGPT_CHECK(q && k && v && o && N >= 1 && heads >= 1 && Lq >= 1 && Lk >= 1, "bad argument");
+    attention(q, q_pitch, k, k_pitch, v, v_pitch, o, o_pitch, N, heads, d, Lq, Lk, (cudaStream_t)stream);
+  });
+}
 int agpt_set_tc_version(int v) { return guarded([&] { tc_set_version(v); }); }
 double agpt_fma_peak_tflops(void) {
   double v = -1.0;

@@ -224,8 +224,14 @@ __global__ void __launch_bounds__(128) attention_kernel(
   }
 }
 
+static int g_attn_tc = -1;
+void attention_set_tc(int on) { g_attn_tc = on; }
+
 void attention(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch,
                float* o, int o_pitch, int N, int heads, int d, int Lq, int Lk, cudaStream_t st) {
+  if (g_attn_tc < 0) { const char* e = getenv("AGPT_ATTN_TC"); g_attn_tc = (e && e[0] == '0') ? 0 : 1; }
+  // tensor-core path (QK^T and PV on tcgen05, attention_tc.cu); the fp32 kernel below is the A/B reference
+  if (g_attn_tc == 1 && attention_tc(q, q_pitch, k, k_pitch, v, v_pitch, o, o_pitch, N, heads, d, Lq, Lk, st)) return;
   const float scale = 1.0f / sqrtf((float)d);   // dim_head ** -0.5  (attention.py:158)
   dim3 grid(cdiv(Lq, 64), heads, N);
 #define AGPT_ATT(DH_) attention_kernel<DH_><<<grid, 128, 0, st>>>(q, q_pitch, k, k_pitch, v, v_pitch, o, o_pitch, Lq, Lk, scale)

@@ -160,14 +160,17 @@ def lpt_assign(costs: Sequence[float], workers: int) -> List[List[int]]:
     return out
 
 
-def run_mixed(jobs: Sequence[Tuple[str, int]], run_job, *, sync=None) -> Dict[str, object]:
+def run_mixed(jobs: Sequence[Tuple[str, int]], run_job, *, sync=None, run_group=None, group_size: Dict[str, int] = None) -> Dict[str, object]:
     """BASELINE configs[4] (mixed dispatch): ``jobs`` = [(kind, frames), ...] known to every rank in the same
     order; greedy-LPT assignment by the FLOP cost model, every rank runs its own jobs with
     ``run_job(index, kind, frames)`` (no data-path collective), then ONE all_gather of the per-rank timings.
 
     Returns, on every rank: ``assignment`` (per-rank job indices), ``busy_s`` (per-rank busy seconds),
     ``makespan_s`` (max over ranks), ``jobs_per_s`` and ``busy_fraction`` (busy / makespan per rank).
-    ``sync`` is called before each clock read (pass ``torch.cuda.synchronize`` on a GPU box)."""
+    ``sync`` is called before each clock read (pass ``torch.cuda.synchronize`` on a GPU box).
+    ``run_group(kind, indices)`` (optional) lets a rank serve its OWN jobs of one kind in micro-batches of at most
+    ``group_size[kind]`` (default 1) -- e.g. four text-to-audio clips as one CFG batch of 8; the assignment itself
+    is unchanged."""
     import time
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
@@ -176,8 +179,18 @@ def run_mixed(jobs: Sequence[Tuple[str, int]], run_job, *, sync=None) -> Dict[st
     if sync:
         sync()
     t0 = time.perf_counter()
-    for i in assignment[rank]:
-        run_job(i, jobs[i][0], jobs[i][1])
+    if run_group is None:
+        for i in assignment[rank]:
+            run_job(i, jobs[i][0], jobs[i][1])
+    else:
+        gs = group_size or {}
+        by_kind: Dict[str, List[int]] = {}
+        for i in assignment[rank]:
+            by_kind.setdefault(jobs[i][0], []).append(i)
+        for kind, idxs in by_kind.items():
+            n = max(1, int(gs.get(kind, 1)))
+            for a in range(0, len(idxs), n):
+                run_group(kind, idxs[a:a + n])
     if sync:
         sync()
     busy = time.perf_counter() - t0

@@ -232,8 +232,9 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------ GPU arm: DDIM (C4)
-def measure_ddim(dev, rank, n_gpus, chains, peaks, want_cpu):
-    """All ranks: DDIM-100 + CFG for DDIM_B clips per rank.  Returns the 'ddim' object (rank 0) or None."""
+def measure_ddim(dev, rank, n_gpus, chains, peaks, want_cpu, keep=None):
+    """All ranks: DDIM-100 + CFG for DDIM_B clips per rank.  Returns the 'ddim' object (rank 0) or None.
+    ``keep`` (a dict) receives the sampler so that the mixed-dispatch measurement can reuse the 160 M-param engine."""
     import ctypes as C
     import torch.distributed as dist
     from audiogpt_b200 import _lib, parallel, specs
@@ -290,6 +291,8 @@ def measure_ddim(dev, rank, n_gpus, chains, peaks, want_cpu):
     L = _lib.lib()
     L.agpt_unet_launches_per_step.restype = C.c_long
     lps = int(L.agpt_unet_launches_per_step(u._h))
+    if keep is not None:
+        keep["sampler"] = smp
     del smp, u
     torch.cuda.empty_cache()
     if rank != 0:
@@ -320,6 +323,57 @@ def measure_ddim(dev, rank, n_gpus, chains, peaks, want_cpu):
                                "sample": f"B=1: 3 of the {DDIM_S} DDIM steps of oracle/ldm_ref.py (CFG pair per step) on {cores} threads; "
                                          f"clips/s = 1 / (s_per_step x {DDIM_S})"}
     return out
+
+
+# ------------------------------------------------------------------------------------ GPU arm: mixed dispatch (C5)
+def measure_mixed(dev, rank, n_gpus, vocoder, sampler):
+    """BASELINE configs[4]: 64 concurrent prompts -- 32 TTS utterances (T ~ U{200..800} mel frames, seed 7, through
+    HiFi-GAN) + 32 text-to-audio clips (DDIM-100 + CFG on the 4x10x78 latent -> AutoencoderKL.decode -> the 80x624 mel
+    through the vocoder) -- assigned to the ranks by greedy LPT on the FLOP cost model (parallel.run_mixed), every
+    rank serving its own jobs with no data-path collective; text-to-audio jobs of a rank run in micro-batches of 4
+    clips.  Returns makespan, jobs/s and per-GPU busy fraction (all ranks get the same dict)."""
+    from audiogpt_b200 import parallel, specs
+    from audiogpt_b200.ldm.models.autoencoder import AutoencoderKL
+    cfgv = specs.VAE_TXT2AUDIO
+    vae = AutoencoderKL(ddconfig={k: v for k, v in cfgv.items() if k != "embed_dim"}, embed_dim=cfgv["embed_dim"])
+    vae.load_state_dict(specs.synth_vae_decoder(cfgv, 5150), strict=False)
+    vae = vae.eval().to(dev)
+    rng = np.random.RandomState(7)
+    jobs = [("tts", int(t)) for t in rng.randint(200, 801, 32)] + [("t2a", 624)] * 32
+    done = {"tts": 0, "t2a": 0, "samples": 0}
+
+    def run_group(kind, idxs):
+        if kind == "tts":
+            for i in idxs:
+                mel = specs.synth_tensor((1, 80, jobs[i][1]), seed=1000 + i, scale=2.0, shift=-4.0).to(dev)
+                done["samples"] += int(vocoder(mel).shape[-1])
+                done["tts"] += 1
+            return
+        B = len(idxs)
+        xT = torch.tensor(np.random.RandomState(55 + idxs[0]).randn(B, *DDIM_SHAPE), dtype=torch.float32).to(dev)
+        c = specs.synth_tensor((B, 77, 1024), seed=2000 + idxs[0]).to(dev)
+        uc = specs.synth_tensor((1, 77, 1024), seed=6).expand(B, -1, -1).contiguous().to(dev)
+        z, _ = sampler.sample(S=DDIM_S, batch_size=B, shape=DDIM_SHAPE, conditioning=c, verbose=False, x_T=xT, eta=0.0,
+                              unconditional_guidance_scale=DDIM_SCALE, unconditional_conditioning=uc)
+        mel = vae.decode(z)[:, 0]                       # [B, 80, 624]
+        done["samples"] += int(vocoder(mel.contiguous()).shape[-1]) * B
+        done["t2a"] += B
+
+    # warm-up of every engine shape class outside the clock (arena sizing, graph capture for the B=4 and tail batches)
+    run_group("t2a", [32, 33, 34, 35])
+    run_group("tts", [0])
+    done.update(tts=0, t2a=0, samples=0)
+    res = parallel.run_mixed(jobs, None, sync=lambda: torch.cuda.synchronize(dev), run_group=run_group,
+                             group_size={"t2a": 4, "tts": 1})
+    del vae
+    torch.cuda.empty_cache()
+    return {"workload": "BASELINE configs[4]: 32 TTS utterances (200..800 frames, HiFi-GAN V1) + 32 text-to-audio clips "
+                        "(DDIM-100 CFG 1.5 -> AutoencoderKL.decode -> HiFi-GAN on the 80x624 mel), greedy LPT over the ranks, "
+                        "text-to-audio in micro-batches of 4 clips per rank",
+            "jobs": len(jobs), "makespan_s": res["makespan_s"], "jobs_per_s": res["jobs_per_s"],
+            "busy_s": res["busy_s"], "busy_fraction": res["busy_fraction"],
+            "model_load_tflop_per_rank": res["model_load_tflop"],
+            "jobs_on_rank0": {"tts": done["tts"], "t2a": done["t2a"]}, "collectives_in_data_path": 0}
 
 
 # ------------------------------------------------------------------------------------ GPU arm: HiFi-GAN
@@ -477,18 +531,25 @@ def run_ours(args):
                 "share_of_step": tot_ms / ms_per_step if n_gpus == 1 else None,
                 "per_variant": per_variant, "hbm": hbm, "traffic": traffic,
             }
-    del model
-    torch.cuda.empty_cache()
-
-    # ---- the other half of the metric: DDIM-100 clips/s on the C4 shard (all ranks)
-    ddim = None
+    # ---- the other half of the metric: DDIM-100 clips/s on the C4 shard (all ranks), then the mixed dispatch (C5)
+    ddim, mixed, keep = None, None, {}
     if not args.no_ddim:
         try:
-            ddim = measure_ddim(dev, rank, n_gpus, args.ddim_chains, peaks, want_cpu=False)
+            ddim = measure_ddim(dev, rank, n_gpus, args.ddim_chains, peaks, want_cpu=False, keep=keep)
         except Exception as ex:
             if n_gpus > 1:
                 raise
             ddim = {"error": repr(ex)}
+        if keep.get("sampler") is not None and not args.no_mixed:
+            try:
+                mixed = measure_mixed(dev, rank, n_gpus, model, keep["sampler"])
+            except Exception as ex:
+                if n_gpus > 1:
+                    raise
+                mixed = {"error": repr(ex)}
+    keep.clear()
+    del model
+    torch.cuda.empty_cache()
     if rank != 0:
         finish()
         return
@@ -521,7 +582,7 @@ def run_ours(args):
             "x_realtime": value * HOP / SR, "x_realtime_per_gpu": value * HOP / SR / n_gpus,
             "tflops_fp32": 0.614e9 * value / 1e12,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "ddim": ddim, "extra": extra}
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "ddim": ddim, "mixed_dispatch": mixed, "extra": extra}
     print(json.dumps(line))
     sys.stdout.flush()
     finish()
@@ -595,6 +656,7 @@ def main():
                          "ddim: the C4 DDIM-100 line alone (steps = timed chains)")
     ap.add_argument("--ddim-chains", type=int, default=2, help="timed DDIM-100 chains of the 'ddim' object (after 1 warm-up chain)")
     ap.add_argument("--no-ddim", action="store_true", help="skip the DDIM C4 measurement")
+    ap.add_argument("--no-mixed", action="store_true", help="skip the mixed-dispatch (BASELINE configs[4]) measurement")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary DiffSinger / BigVGAN measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

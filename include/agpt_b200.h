@@ -46,6 +46,14 @@ int agpt_set_tensor_cores(int on);
  * one-tile-per-CTA kernel (tcconv5) otherwise; 5 = tcconv5 only; 7 = tcconv6 forced; -1 = environment
  * (AGPT_TC_V) / default.                                                                               */
 int agpt_set_tc_version(int v);
+/* Multi-head attention softmax_j(q_i . k_j * d^-0.5) v_j, heads outermost in the channel dim ('b n (h d)'),
+ * CrossAttention.forward (ldm/modules/attention.py:170-193): q [N][Lq][q_pitch], k / v [N][Lk][pitch] device rows with
+ * head h at channels [h*d, (h+1)*d); o [N][Lq][o_pitch].  Default: QK^T and PV on the tcgen05 tensor cores
+ * (error-compensated fp16 parts, fp32 accumulation, exact online softmax; d in {8,16,32,40,64,80});
+ * agpt_set_attention_tc(0) / AGPT_ATTN_TC=0 selects the fp32-FMA kernel.                                        */
+int agpt_attention(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, float* o,
+                   int o_pitch, int N, int heads, int d, int Lq, int Lk, void* stream);
+int agpt_set_attention_tc(int on);
 /* Micro-benchmark of one tapconv layer (random data): out3 = {ms per launch, algorithmic TFLOP/s,
  * max |tcgen05 - fp32 FMA| when check != 0}; dbg8 (tcgen05 only) = average per-CTA phase cycles
  * {setup, first activation tile, MMA issue loop, drain, epilogue, total, wait-on-activations,

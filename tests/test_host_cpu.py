@@ -204,6 +204,13 @@ assert sorted(res["assignment"][0] + res["assignment"][1]) == list(range(8))
 assert done == res["assignment"][rank] and len(res["busy_s"]) == 2
 assert res["makespan_s"] >= max(res["busy_s"]) - 1e-9 and abs(max(res["busy_fraction"]) - 1.0) < 1e-9
 assert abs(res["model_load_tflop"][0] - res["model_load_tflop"][1]) < 1.0     # one t2a clip (~19 TFLOP) on each rank
+# grouped service: a rank serves its own jobs of one kind in micro-batches (the bench's text-to-audio batches of 4)
+groups = []
+res2 = parallel.run_mixed([("tts", 300)] * 4 + [("t2a", 0)] * 6, None, run_group=lambda kind, idxs: groups.append((kind, list(idxs))),
+                          group_size=dict(t2a=2))
+mine = res2["assignment"][rank]
+assert sorted(i for _, g in groups for i in g) == sorted(mine)
+assert all(len(g) <= (2 if k == "t2a" else 1) for k, g in groups) and sum(len(g) for k, g in groups if k == "t2a") == 3
 print("rank", rank, "ok", flush=True)
 import torch.distributed as dist
 dist.barrier()

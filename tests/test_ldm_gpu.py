@@ -182,3 +182,34 @@ def test_c4_full_size_properties():
     assert e.shape == (8, 4, 10, 78) and torch.isfinite(e).all()
     e1 = u(x[2:3].contiguous(), timesteps=[501], context=ctx[2:3].contiguous())
     assert torch.allclose(e1[0], e[2], atol=2e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("N,heads,d,Lq,Lk", [(2, 8, 40, 780, 780), (2, 8, 40, 780, 77), (2, 8, 80, 195, 195), (1, 8, 80, 195, 77),
+                                             (1, 2, 8, 5, 3), (2, 3, 16, 130, 70), (1, 4, 32, 64, 129), (1, 2, 64, 200, 64)])
+def test_tensor_core_attention_vs_fp64(N, heads, d, Lq, Lk):
+    """agpt_attention (QK^T and PV on tcgen05, online softmax) against softmax(q k^T d^-0.5) v evaluated in fp64, for the
+    UNet's shapes (8 heads of 40 / 80 channels; 780 / 195 queries; 780 / 195 / 77 keys) and ragged small ones; the
+    fp32-FMA kernel is held to the same gate.  Stated tolerance: rel-RMSE <= 1e-5 (3 x fp16-part products, 2^-22)."""
+    import ctypes as C
+    from audiogpt_b200 import _lib
+    L = _lib.lib()
+    C_ = heads * d
+    q = specs.synth_tensor((N, Lq, C_), seed=1).cuda()
+    kv = specs.synth_tensor((N, Lk, 2 * C_), seed=2).cuda()            # K | V interleaved rows, like the hoisted context projection
+    qh = q.double().cpu().reshape(N, Lq, heads, d).permute(0, 2, 1, 3)
+    kh = kv[:, :, :C_].double().cpu().reshape(N, Lk, heads, d).permute(0, 2, 1, 3)
+    vh = kv[:, :, C_:].double().cpu().reshape(N, Lk, heads, d).permute(0, 2, 1, 3)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) * d ** -0.5, dim=-1) @ vh).permute(0, 2, 1, 3).reshape(N, Lq, C_)
+    errs = []
+    for tc in (1, 0):
+        _lib.check(L.agpt_set_attention_tc(tc))
+        try:
+            o = torch.full((N, Lq, C_), float("nan"), device="cuda")
+            _lib.check(L.agpt_attention(_lib.fptr(q), C_, _lib.fptr(kv), 2 * C_, C.c_void_p(kv.data_ptr() + 4 * C_), 2 * C_,
+                                        _lib.fptr(o), C_, N, heads, d, Lq, Lk, _lib.cur_stream()))
+            torch.cuda.synchronize()
+        finally:
+            _lib.check(L.agpt_set_attention_tc(-1))
+        errs.append(rel_rmse(o.cpu(), ref))
+    print(f"attention N={N} h={heads} d={d} {Lq}x{Lk}: rel-RMSE tcgen05 {errs[0]:.2e}  fp32 kernel {errs[1]:.2e}")
+    assert errs[0] < 1e-5 and errs[1] < 1e-5
