@@ -52,11 +52,30 @@ void bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, i
     P.tc_flags_user = 2;
   }
   cudaStream_t st = nullptr;
-  for (int i = 0; i < 2; ++i) tapconv_launch(P, st);
+  // version 8: the plane-fed kernel (tcconv7.cu) -- planes of lrelu(x) in, fp32 result + planes of lrelu(result) out
+  const bool planes_mode = use_tc && tc_get_version() == 8;
+  DevBuf pin, pout;
+  PlaneIO PQ;
+  memset(&PQ, 0, sizeof(PQ));
+  if (planes_mode) {
+    AGPT_CHECK(!is2d, "the plane-fed kernel handles 1-D layers");
+    pin.ensure(nin + 8); pout.ensure(nout + 8);      // two fp16 planes = one fp32 tensor's bytes
+    __half* ih = reinterpret_cast<__half*>(pin.p); __half* il = ih + nin;
+    __half* oh = reinterpret_cast<__half*>(pout.p); __half* ol = oh + nout;
+    make_planes(x.p, ih, il, (long)nin, PRO_LRELU, 0.1f, st);
+    PQ.in_hi = ih; PQ.in_lo = il; PQ.in_gstride = (long)L * Cin; PQ.in_pitch = Cin;
+    PQ.out_hi = oh; PQ.out_lo = ol; PQ.outp_gstride = (long)L * Cout; PQ.outp_pitch = Cout;
+    PQ.out_pro = PRO_LRELU; PQ.out_slope = 0.1f; PQ.store_f32 = 1;
+  }
+  auto launch = [&]() {
+    if (planes_mode) { AGPT_CHECK(tcconv7_launch(P, PQ, st), "the plane-fed kernel rejected this layer"); count_launch(1); }
+    else tapconv_launch(P, st);
+  };
+  for (int i = 0; i < 2; ++i) launch();
   cudaEvent_t e0, e1;
   AGPT_CUDA(cudaEventCreate(&e0)); AGPT_CUDA(cudaEventCreate(&e1));
   AGPT_CUDA(cudaEventRecord(e0, st));
-  for (int i = 0; i < reps; ++i) tapconv_launch(P, st);
+  for (int i = 0; i < reps; ++i) launch();
   AGPT_CUDA(cudaEventRecord(e1, st));
   AGPT_CUDA(cudaEventSynchronize(e1));
   float ms = 0.f;
@@ -113,6 +132,18 @@ void bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, i
       const double rms = std::sqrt(sr / (double)nout);
       rel2[0] = finite ? (rms > 0 ? mx / rms : mx) : 1e30;
       rel2[1] = finite ? (rms > 0 ? std::sqrt(se / (double)nout) / rms : std::sqrt(se / (double)nout)) : 1e30;
+      if (planes_mode) {   // the emitted planes must hold lrelu(fp32 result): hi + lo == prologue(out) to 2^-21 relative
+        std::vector<__half> ph(nout), pl(nout);
+        AGPT_CUDA(cudaMemcpy(ph.data(), PQ.out_hi, nout * 2, cudaMemcpyDeviceToHost));
+        AGPT_CUDA(cudaMemcpy(pl.data(), PQ.out_lo, nout * 2, cudaMemcpyDeviceToHost));
+        double pm = 0;
+        for (size_t i = 0; i < nout; ++i) {
+          const float ref = a[i] > 0.f ? a[i] : 0.1f * a[i];
+          const double got = (double)__half2float(ph[i]) + (double)__half2float(pl[i]);
+          pm = std::max(pm, std::fabs(got - (double)ref) / std::max(1e-3, std::fabs((double)ref)));
+        }
+        rel2[0] = std::max(rel2[0], pm > 1e-6 ? pm : 0.0);     // a plane error above 1e-6 relative fails the caller's gate
+      }
     }
   }
   tc_set_enabled(tc_prev ? 1 : 0);

@@ -18,6 +18,7 @@
 // ONCE per chunk in shared memory in four row-shifted copies so that every tap is read
 // with aligned 128-bit LDS; weight slabs [8][BN] stream through a cp.async double buffer.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace agpt {
@@ -92,6 +93,16 @@ __host__ __device__ inline int tc_row_out(const TapConvParams& P, int gz, int q,
   }
   return j < P.Wreal ? h * P.Wreal + j : -1;
 }
+
+// Operand planes of the plane-fed kernel (tcconv7.cu): fp16 hi/lo parts of prologue(x), [G][L][C] each.
+struct PlaneIO {
+  const __half* in_hi; const __half* in_lo; long in_gstride; int in_pitch;       // operand planes of the input
+  __half* out_hi; __half* out_lo; long outp_gstride; int outp_pitch;             // planes to emit (nullptr: none)
+  int out_pro; float out_slope;                                                  // consumer prologue applied before the split
+  int store_f32;                                                                 // also store the fp32 result (residual / accumulator use)
+};
+bool tcconv7_launch(TapConvParams P, const PlaneIO& Q, cudaStream_t st);
+void make_planes(const float* x, __half* hi, __half* lo, long n, int pro, float slope, cudaStream_t st);
 
 // ---------------------------------------------------------------- host side
 struct PackedConv {

@@ -48,7 +48,7 @@ int tc_get_version() {
   if (ver < 0) {
     const char* e = getenv("AGPT_TC_V");
     ver = e ? atoi(e) : 6;   // 6 (default): v6 where a CTA gets more than one tile, else v5; 5: v5 only; 7: v6 forced
-    if (ver < 5) ver = 6;
+    if (ver < 5 || ver > 8) ver = 6;     // 8: dev / test selector of the plane-fed kernel in agpt_bench_tapconv (else = 6)
   }
   static bool env_done = false;
   if (!env_done) {
