@@ -53,7 +53,12 @@ def install(strict: bool = False):
             patched.append(ref_name + " (aliased)")
             continue
         for a in attrs:
-            setattr(ref, a, getattr(ours, a))
+            theirs = getattr(ref, a, None)
+            mine = getattr(ours, a)
+            # configs the drop-in does not cover (e.g. the inpainting AttentionBlock UNet) keep the reference class
+            if hasattr(mine, "_reference_cls") and isinstance(theirs, type) and theirs is not mine:
+                mine._reference_cls = theirs
+            setattr(ref, a, mine)
         patched.append(ref_name)
     # the vocoder registry of the reference keeps its own dict: register ours there too
     try:

@@ -331,6 +331,8 @@ struct Hifigan : Handle {
   AaFilter aaf;                     // the 12 Kaiser-sinc taps (state-dict buffer)
   int c_last = 0, hop = 1;
   DevBuf melT, buf[6], sbuf;        // sbuf: activated conv input (BigVGAN only)
+  DevBuf pbuf[5];                   // operand planes (fp16 hi | lo = one fp32 tensor's bytes each): cur, X, A, R0, R1
+  bool planes_ok = false;           // every ResBlock conv fits the plane-fed kernel (halo <= 128 rows)
   DevBuf io_mel, io_wav, io_har;  // staging for the host-buffer entry point
   float* pin_mel = nullptr; float* pin_wav = nullptr; size_t pin_mel_n = 0, pin_wav_n = 0;
   cudaStream_t own_stream = nullptr;
@@ -341,8 +343,122 @@ struct Hifigan : Handle {
     if (own_stream) cudaStreamDestroy(own_stream);
   }
 
+  // ---- plane mode (default for HiFi-GAN without NSF excitation): every tensor that feeds a conv exists as fp16 hi/lo
+  // OPERAND PLANES of leaky_relu(x, 0.1), written by the producing conv's epilogue; the convs run on the plane-fed
+  // kernel (tcconv7.cu: TMA -> tcgen05, no transform warps).  Data flow per ResBlock1 pair (hifigan.py:54-61):
+  //   c1: P(x) -> P(A) only (A is never needed in fp32);  c2: P(A) + residual x (fp32) -> x' fp32 + P(x');
+  //   the last pair reduce-adds x'/3 into the MRF accumulator, whose planes are made by one light pass per stage.
+  struct Planes { __half* hi; __half* lo; };
+  Planes planes_of(DevBuf& b, size_t elems) {
+    float* p = b.ensure(elems + 8);
+    __half* h = reinterpret_cast<__half*>(p);
+    return Planes{h, h + elems};
+  }
+  bool conv_planes(const PackedConv& pc, int Bn, long L, int Cin_, int dil, Planes in, float* out_f32, int out_pitch, long out_gs,
+                   Planes* outp, int epi, const float* res_, float scale, int accumulate, cudaStream_t st) {
+    TapConvParams P = tapconv_params(pc, Bn, (int)L, 0, dil);
+    P.in = nullptr; P.in_gstride = L * Cin_; P.in_pitch = Cin_;
+    P.out = out_f32; P.out_gstride = out_gs; P.out_pitch = out_pitch;
+    P.pro = PRO_NONE; P.epi = epi; P.scale = scale; P.accumulate = accumulate;
+    P.res = res_; P.res_gstride = out_gs; P.res_pitch = out_pitch;
+    PlaneIO Q;
+    memset(&Q, 0, sizeof(Q));
+    Q.in_hi = in.hi; Q.in_lo = in.lo; Q.in_gstride = L * Cin_; Q.in_pitch = Cin_;
+    if (outp) { Q.out_hi = outp->hi; Q.out_lo = outp->lo; Q.outp_gstride = out_gs; Q.outp_pitch = out_pitch; }
+    Q.out_pro = PRO_LRELU; Q.out_slope = 0.1f;
+    Q.store_f32 = out_f32 != nullptr ? 1 : 0;
+    const double rows = (double)Bn * (double)L;
+    const double bytes = 4.0 * rows * Cin_ /* hi + lo planes */ + (Q.store_f32 ? 4.0 * rows * pc.Cout : 0.0) +
+                         (outp ? 4.0 * rows * pc.Cout : 0.0) + (res_ ? 4.0 * rows * pc.Cout : 0.0) +
+                         (epi == EPI_ACC && accumulate ? 4.0 * rows * pc.Cout : 0.0) + 4.0 * pc.ntaps * pc.Cin * pc.Cout;
+    void* rec = profile_begin(P, true, bytes, st);
+    if (!tcconv7_launch(P, Q, st)) return false;
+    profile_end(rec, st);
+    count_launch(1);
+    AGPT_CUDA(cudaGetLastError());
+    return true;
+  }
+
+  void forward_planes(const float* mel, int B, int T, float* wav, cudaStream_t st) {
+    const int C0 = cfg.upsample_initial_channel;
+    size_t mx = (size_t)T * C0;
+    {
+      long L = T; int C = C0;
+      for (int i = 0; i < cfg.num_upsamples; ++i) { L *= cfg.upsample_rates[i]; C /= 2; mx = std::max(mx, (size_t)L * C); }
+    }
+    mx *= (size_t)B;
+    for (int i = 0; i < 6; ++i) if (i != 3) buf[i].ensure(mx);     // buf[3] (the fp32 c1 output) is not needed
+    melT.ensure((size_t)B * T * cfg.n_mels);
+    float *cur = buf[0].p, *acc = buf[1].p, *X = buf[2].p, *R0 = buf[4].p, *R1 = buf[5].p;
+    Planes Pcur = planes_of(pbuf[0], mx), PX = planes_of(pbuf[1], mx), PA = planes_of(pbuf[2], mx);
+    Planes PR[2] = {planes_of(pbuf[3], mx), planes_of(pbuf[4], mx)};
+    launch_cf_to_cl(mel, melT.p, B, cfg.n_mels, T, st);
+    {
+      TapConvParams P = tapconv_params(conv_pre, B, T, 0, 1);
+      P.in = melT.p; P.in_gstride = (long)T * cfg.n_mels; P.in_pitch = cfg.n_mels;
+      P.out = cur; P.out_gstride = (long)T * C0; P.out_pitch = C0;
+      P.pro = PRO_NONE; P.epi = EPI_BIAS;
+      tapconv_launch(P, st);
+    }
+    long L = T; int C = C0;
+    const float inv_nk = 1.f / (float)cfg.num_kernels;
+    for (int i = 0; i < cfg.num_upsamples; ++i) {
+      const int u = cfg.upsample_rates[i];
+      const int Co = C / 2;
+      make_planes(cur, Pcur.hi, Pcur.lo, (long)B * L * C, PRO_LRELU, 0.1f, st);
+      // leaky_relu(0.1) -> ConvTranspose1d (polyphase: u * Co output channels per input row); X fp32 + P(X)
+      AGPT_CHECK(conv_planes(ups[i], B, L, C, 1, Pcur, X, u * Co, L * u * Co, &PX, EPI_BIAS, nullptr, 1.f, 0, st),
+                 "plane-fed kernel rejected an upsample layer");
+      L *= u; C = Co;
+      const long gs = L * C;
+      for (int j = 0; j < cfg.num_kernels; ++j) {
+        const ResBlockW& rb = rbs[i * cfg.num_kernels + j];
+        const float* x = X;
+        Planes px = PX;
+        const int nd = (int)rb.dil.size();
+        for (int n = 0; n < nd; ++n) {
+          const bool last = (n == nd - 1);
+          float* dst = last ? acc : ((n & 1) ? R1 : R0);
+          Planes pin = px;
+          if (cfg.resblock_type == 1) {
+            AGPT_CHECK(conv_planes(rb.c1[n], B, L, C, rb.dil[n], px, nullptr, C, gs, &PA, EPI_BIAS, nullptr, 1.f, 0, st),
+                       "plane-fed kernel rejected a ResBlock conv");
+            pin = PA;
+          }
+          const PackedConv& pc = (cfg.resblock_type == 1) ? rb.c2[n] : rb.c1[n];
+          const int d2 = (cfg.resblock_type == 1) ? 1 : rb.dil[n];
+          bool ok;
+          if (last) ok = conv_planes(pc, B, L, C, d2, pin, dst, C, gs, nullptr, EPI_ACC, x, inv_nk, j > 0 ? 1 : 0, st);
+          else ok = conv_planes(pc, B, L, C, d2, pin, dst, C, gs, &PR[n & 1], EPI_RES, x, 1.f, 0, st);
+          AGPT_CHECK(ok, "plane-fed kernel rejected a ResBlock conv");
+          x = dst; px = PR[n & 1];
+        }
+      }
+      std::swap(cur, acc);
+    }
+    {
+      const int threads = 256;
+      dim3 grid(cdiv((int)L, threads), B);
+      const size_t smem = (size_t)cfg.c_out * 7 * C * sizeof(float);
+      if (C == 32 && smem <= 8 * 1024)
+        conv_post32_kernel<<<grid, CP_ROWS, smem, st>>>(cur, post_w.p, post_b.p, wav, (int)L, cfg.c_out, 0.01f);
+      else
+        conv_post_kernel<<<grid, threads, smem, st>>>(cur, post_w.p, post_b.p, wav, (int)L, C, cfg.c_out, 0.01f);
+      count_launch(1);
+      AGPT_CUDA(cudaGetLastError());
+    }
+  }
+
   void forward(const float* mel, const float* har, int B, int T, float* wav, cudaStream_t st) {
     AGPT_CHECK(B >= 1 && T >= 1, "empty batch");
+    {
+      static int allow_planes = -1;
+      if (allow_planes < 0) { const char* e = getenv("AGPT_PLANES"); allow_planes = (e && e[0] == '0') ? 0 : 1; }
+      if (allow_planes && planes_ok && !har && cfg.activation == 0 && tc_enabled() && tc_get_version() >= 6) {
+        forward_planes(mel, B, T, wav, st);
+        return;
+      }
+    }
     const int C0 = cfg.upsample_initial_channel;
     // buffer sizing: max over stages of L_i * C_i
     size_t mx = (size_t)T * C0;
@@ -500,6 +616,21 @@ Handle* hifigan_create(const agpt_hifigan_cfg* cfg, const float* const* W, int n
         for (auto& a : rb.act) load_snake(a, C);
       }
     }
+  }
+  {  // plane mode needs every ResBlock conv's halo inside one tensor-map box (128 + (k-1)*dil <= 256 rows),
+     // 16-byte aligned fp16 rows (channels % 8) and channel counts the TMA epilogue's 32-column boxes cover
+    bool ok = true;
+    int Cc = C0;
+    for (int i = 0; i < nu; ++i) {
+      Cc /= 2;
+      if (Cc % 32 != 0) ok = false;
+      for (int j = 0; j < nk; ++j) {
+        const ResBlockW& rb = h->rbs[i * nk + j];
+        for (int d : rb.dil) if ((rb.ks - 1) * d > 120) ok = false;
+      }
+    }
+    if (C0 % 32 != 0) ok = false;
+    h->planes_ok = ok;
   }
   if (cfg->activation != 0) load_snake(h->act_post, C);
   {  // conv_post [c_out][C][7] -> [c_out][7][C]

@@ -230,6 +230,34 @@ static void fma_launch(TapConvParams P, cudaStream_t st) {
   else tapconv_kernel<32><<<grid, 64, smem, st>>>(P);
 }
 
+// Per-launch profiling record (bench.py's roofline leg): algorithmic FLOPs and bytes of one tap-GEMM launch.
+// bytes_override > 0 replaces the fp32-tensor byte model (the plane-fed kernel moves fp16 planes).
+void* profile_begin(const TapConvParams& P, bool tc, double bytes_override, cudaStream_t st) {
+  if (!g_prof) return nullptr;
+  g_recs.emplace_back();
+  ProfRec* rec = &g_recs.back();
+  const int bn = tc_pick_bn(P.Cout);
+  rec->variant = tc ? 3 : (bn == 128 ? 0 : (bn == 64 ? 1 : 2));
+  const double rows = (double)P.G * P.L;
+  rec->flops = 2.0 * rows * P.Cin * P.Cout * P.ntaps * (P.flops_scale > 0.f ? P.flops_scale : 1.f);
+  const int out_c = (P.epi == EPI_GATE || P.epi == EPI_GEGLU) ? P.Cout / 2 : P.Cout;
+  rec->bytes = bytes_override > 0 ? bytes_override
+                                  : 4.0 * (rows * P.Cin + rows * out_c + (P.res ? rows * P.Cout : 0.0) +
+                                           (P.epi == EPI_ACC && P.accumulate ? rows * P.Cout : 0.0) +
+                                           (double)P.ntaps * P.Cin * P.Cout);
+  rec->G = P.G; rec->L = P.L; rec->Cin = P.Cin; rec->Cout = P.Cout; rec->ntaps = P.ntaps; rec->epi = P.epi; rec->Wreal = P.Wreal;
+  { int lo = P.tap_off[0], hi = P.tap_off[0];
+    for (int t = 1; t < P.ntaps; ++t) { lo = std::min(lo, P.tap_off[t]); hi = std::max(hi, P.tap_off[t]); }
+    rec->span = hi - lo; }
+  AGPT_CUDA(cudaEventCreate(&rec->e0));
+  AGPT_CUDA(cudaEventCreate(&rec->e1));
+  AGPT_CUDA(cudaEventRecord(rec->e0, st));
+  return rec;
+}
+void profile_end(void* r, cudaStream_t st) {
+  if (r) AGPT_CUDA(cudaEventRecord(static_cast<ProfRec*>(r)->e1, st));
+}
+
 // Dispatch: tcgen05 version when the layer has a tensor-core weight image and the operands are
 // 16-byte addressable, else the fp32-FMA version.  Both are sm_100a CUDA; there is no other path.
 void tapconv_launch(TapConvParams P, cudaStream_t st) {
@@ -237,29 +265,10 @@ void tapconv_launch(TapConvParams P, cudaStream_t st) {
   AGPT_CHECK(P.cin_pad % TC_KC == 0 && P.cout_pad % 4 == 0, "padding");
   AGPT_CHECK(P.epi == EPI_STORE_CF || P.out_pitch % (P.epi == EPI_GATE || P.epi == EPI_GEGLU ? 2 : 4) == 0, "pitch");
   const bool tc = tcconv_supported(P);
-  ProfRec* rec = nullptr;
-  if (g_prof) {
-    g_recs.emplace_back();
-    rec = &g_recs.back();
-    const int bn = tc_pick_bn(P.Cout);
-    rec->variant = tc ? 3 : (bn == 128 ? 0 : (bn == 64 ? 1 : 2));
-    const double rows = (double)P.G * P.L;
-    rec->flops = 2.0 * rows * P.Cin * P.Cout * P.ntaps * (P.flops_scale > 0.f ? P.flops_scale : 1.f);
-    const int out_c = (P.epi == EPI_GATE || P.epi == EPI_GEGLU) ? P.Cout / 2 : P.Cout;
-    rec->bytes = 4.0 * (rows * P.Cin + rows * out_c + (P.res ? rows * P.Cout : 0.0) +
-                        (P.epi == EPI_ACC && P.accumulate ? rows * P.Cout : 0.0) +
-                        (double)P.ntaps * P.Cin * P.Cout);
-    rec->G = P.G; rec->L = P.L; rec->Cin = P.Cin; rec->Cout = P.Cout; rec->ntaps = P.ntaps; rec->epi = P.epi; rec->Wreal = P.Wreal;
-    { int lo = P.tap_off[0], hi = P.tap_off[0];
-      for (int t = 1; t < P.ntaps; ++t) { lo = std::min(lo, P.tap_off[t]); hi = std::max(hi, P.tap_off[t]); }
-      rec->span = hi - lo; }
-    AGPT_CUDA(cudaEventCreate(&rec->e0));
-    AGPT_CUDA(cudaEventCreate(&rec->e1));
-    AGPT_CUDA(cudaEventRecord(rec->e0, st));
-  }
+  void* rec = profile_begin(P, tc, 0.0, st);
   if (tc) tcconv_launch(P, st);
   else fma_launch(P, st);
-  if (rec) AGPT_CUDA(cudaEventRecord(rec->e1, st));
+  profile_end(rec, st);
   count_launch(1);
   AGPT_CUDA(cudaGetLastError());
 }

@@ -139,6 +139,8 @@ void tc_set_version(int v);
 int tc_get_version();
 bool tc_enabled();
 void profile_enable(int on);
+void* profile_begin(const TapConvParams& P, bool tc, double bytes_override, cudaStream_t st);
+void profile_end(void* rec, cudaStream_t st);
 void profile_collect(double* ms, double* flops, double* bytes, long long* launches);
 long profile_dump(char* out, long cap);
 double fma_peak_tflops();

@@ -254,7 +254,7 @@ tcconv7_kernel(const __grid_constant__ TapConvParams P, const __grid_constant__ 
       tma_load_3d(smem + S.stg + bi * V7_EBLK, &tm_res, T.ct * BN + 32 * b, T.q0, T.g, &e_full[bi]);
     };
     if (leader) {
-      tma_prefetch_desc(&tm_out);
+      if (f32_out) tma_prefetch_desc(&tm_out);
       if (planes) { tma_prefetch_desc(&tm_phi); tma_prefetch_desc(&tm_plo); }
       if (has_res) {
         tma_prefetch_desc(&tm_res);
@@ -280,7 +280,7 @@ tcconv7_kernel(const __grid_constant__ TapConvParams P, const __grid_constant__ 
       bool acc_ready = false;
 #pragma unroll 1
       for (int cb = 0; cb < BN; cb += 32, ++j) {
-        const int bi = j % NB;
+        const int bi = NB > 0 ? j % NB : 0;
         // Group accounting: every block commits ONE bulk group (fp32 store and/or the two plane stores), so
         // "wait_group.read 1" = everything of block j-2 has left shared memory: its fp32 buffer (== the buffer of
         // block j+LA) and its plane buffer (== the plane buffer of block j, two plane buffers alternate).
@@ -441,11 +441,15 @@ bool tcconv7_launch(TapConvParams P, const PlaneIO& Q, cudaStream_t st) {
   const long abytes = 2L * RRA * 128, wbytes = (long)tps * 2L * BN * 128;
   const long fixed = 1024 + 4 * 256 * 4 + 48 * 8 + 64 + (planes ? 4L * V7_PBLK : 0);
   // no transform registers / raw buffers any more: the budget goes to a deeper operand and epilogue ring
-  int NB = 4, NA = 2, NW = 0;
-  for (; NB >= 2; --NB) {
+  // fp32 block buffers only where the epilogue moves fp32 data (a planes-only layer without residual needs none:
+  // its 64 KB go to the weight / operand rings)
+  const bool need_f32 = Q.store_f32 || has_res;
+  const int stages_per_tile = P.tc_chunks_h * cdiv(P.ntaps, tps);
+  int NB = need_f32 ? 4 : 0, NA = 2, NW = 0;
+  for (;; --NB) {
     const long avail = (long)kMaxDyn7 - fixed - (long)NB * V7_EBLK - NA * abytes;
     NW = (int)std::min<long>(MAX_NW7, avail / wbytes);
-    if (NW >= 2) break;
+    if (NW >= std::min(3, std::max(2, stages_per_tile)) || NB <= (need_f32 ? 2 : 0)) break;
   }
   if (NW < 2) return false;
   while (NA < MAX_NA7 && (long)kMaxDyn7 - fixed - (long)NB * V7_EBLK - (NA + 1) * abytes >= std::max(NW, 3) * wbytes) ++NA;

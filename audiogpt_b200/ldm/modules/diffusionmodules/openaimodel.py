@@ -25,7 +25,36 @@ from torch import nn
 from .... import _lib, paramtree, specs
 
 
+def _unsupported(kw):
+    """Constructor options outside what the shipped txt2audio config uses."""
+    bad = []
+    if kw.get("dims", 2) != 2: bad.append("dims != 2")
+    if not kw.get("conv_resample", True): bad.append("conv_resample=False")
+    if kw.get("num_classes") is not None: bad.append("class-conditional (num_classes)")
+    if kw.get("use_fp16", False): bad.append("use_fp16")
+    if kw.get("use_scale_shift_norm", False): bad.append("use_scale_shift_norm")
+    if kw.get("resblock_updown", False): bad.append("resblock_updown")
+    if not kw.get("use_spatial_transformer", False): bad.append("use_spatial_transformer=False (AttentionBlock UNets)")
+    if kw.get("n_embed") is not None: bad.append("n_embed / predict_codebook_ids")
+    if kw.get("context_dim") is None: bad.append("context_dim=None")
+    if kw.get("num_heads", -1) == -1 and kw.get("num_head_channels", -1) == -1: bad.append("neither num_heads nor num_head_channels")
+    return bad
+
+
 class UNetModel(nn.Module, _lib.HandleOwner):
+    # Set by audiogpt_b200.install(): the reference's own UNetModel class.  AudioGPT also builds UNets this back-end
+    # does not cover (the inpainting model's AttentionBlock UNet, openaimodel.py:278-410); since install() replaces the
+    # class object inside the reference module, constructing one of THOSE configs returns an instance of the
+    # reference's class instead of failing -- those tools keep working exactly as before, un-accelerated.
+    # This is a routing of unsupported model VARIANTS, not a fallback of the accelerated path: a supported config
+    # never leaves the CUDA engine, and without install() (no reference class known) unsupported configs raise.
+    _reference_cls = None
+
+    def __new__(cls, *args, **kwargs):
+        if cls is UNetModel and cls._reference_cls is not None and not args and _unsupported(kwargs):
+            return cls._reference_cls(**kwargs)
+        return super().__new__(cls)
+
     def __init__(self, image_size=None, in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2,
                  attention_resolutions=(1, 2), dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2,
                  num_classes=None, use_checkpoint=False, use_fp16=False, num_heads=-1, num_head_channels=-1,
@@ -34,17 +63,10 @@ class UNetModel(nn.Module, _lib.HandleOwner):
                  context_dim=None, n_embed=None, legacy=True):
         nn.Module.__init__(self)
         _lib.HandleOwner.__init__(self)
-        unsupported = []
-        if dims != 2: unsupported.append("dims != 2")
-        if not conv_resample: unsupported.append("conv_resample=False")
-        if num_classes is not None: unsupported.append("class-conditional (num_classes)")
-        if use_fp16: unsupported.append("use_fp16")
-        if use_scale_shift_norm: unsupported.append("use_scale_shift_norm")
-        if resblock_updown: unsupported.append("resblock_updown")
-        if not use_spatial_transformer: unsupported.append("use_spatial_transformer=False (AttentionBlock UNets)")
-        if n_embed is not None: unsupported.append("n_embed / predict_codebook_ids")
-        if context_dim is None: unsupported.append("context_dim=None")
-        if num_heads == -1 and num_head_channels == -1: unsupported.append("neither num_heads nor num_head_channels")
+        unsupported = _unsupported(dict(dims=dims, conv_resample=conv_resample, num_classes=num_classes, use_fp16=use_fp16,
+                                        use_scale_shift_norm=use_scale_shift_norm, resblock_updown=resblock_updown,
+                                        use_spatial_transformer=use_spatial_transformer, n_embed=n_embed,
+                                        context_dim=context_dim, num_heads=num_heads, num_head_channels=num_head_channels))
         if unsupported:
             raise NotImplementedError("audiogpt_b200.UNetModel does not support: " + ", ".join(unsupported))
         if isinstance(context_dim, (list, tuple)) or type(context_dim).__name__ == "ListConfig":

@@ -203,6 +203,59 @@ def test_cond_cache_survives_freed_source():
     assert not torch.equal(outs[0], outs[1])
 
 
+def test_forward_infer_shallow_diffusion_vs_oracle(monkeypatch):
+    """GaussianDiffusion.forward(infer=True) (shallow_diffusion_tts.py:248-277) end to end: a stub acoustic front-end
+    supplies decoder_inp / mel_out, then the shallow-diffusion start x = q_sample(norm(fs2_mel), K-1), the K-step
+    ancestral loop, denorm_spec and the mel2ph mask -- against the same composition on the CPU oracle with the SAME
+    random draws (torch.randn_like and noise_like are pinned for the call).  Tolerance: rel-RMSE <= 1e-3 on the mel."""
+    from oracle import diffusion_ref as dr
+    cfg = specs.DIFFNET_SMALL
+    K, B, Tn = 30, 2, 23
+    gd = make(cfg, 2024)
+    gd.K_step = K
+    set_hparams_from_dict(dict(cfg, keep_bins=80, schedule_type="linear", max_beta=0.06, gaussian_start=False, pndm_speedup=None))
+    dec = specs.synth_tensor((B, Tn, cfg["hidden_size"]), seed=81)
+    fs2_mel = specs.synth_tensor((B, Tn, 80), seed=82, scale=1.0, shift=-2.5)
+    mel2ph = torch.ones(B, Tn, dtype=torch.long)
+    mel2ph[1, -5:] = 0                                  # padded tail of the second utterance
+
+    class StubFS2(torch.nn.Module):
+        def forward(self, txt_tokens, mel2ph=None, spk_embed=None, ref_mels=None, f0=None, uv=None, energy=None,
+                    skip_decoder=False, infer=False, **kw):
+            return {"decoder_inp": dec.cuda(), "mel_out": fs2_mel.cuda()}
+
+    gd.fs2 = StubFS2()
+    qn = specs.synth_tensor((B, 1, 80, Tn), seed=83)
+    bank = specs.synth_tensor((K, B, 1, 80, Tn), seed=84)
+    calls = []
+
+    def pinned_noise(shape, device, repeat=False):
+        i = K - 1 - len(calls)
+        calls.append(i)
+        return bank[i].to(device)
+
+    monkeypatch.setattr(sdt, "noise_like", pinned_noise)
+    monkeypatch.setattr(torch, "randn_like", lambda x, **kw: qn.to(x.device))
+    ret = gd(torch.zeros(B, 5, dtype=torch.long).cuda(), mel2ph=mel2ph.cuda(), infer=True)
+    monkeypatch.undo()
+    assert calls == list(range(K - 1, -1, -1)) and ret["mel_out"].shape == (B, Tn, 80)
+    assert torch.equal(ret["fs2_mel"].cpu(), fs2_mel)
+    # oracle composition
+    sd = specs.synth_diffnet(cfg, 2024)
+    tab = dr.schedule_tables(dr.linear_betas(100, 0.06))
+    smin, smax = T(specs.SPEC_MIN)[None, None], T(specs.SPEC_MAX)[None, None]
+    cond = dec.transpose(1, 2)
+    x = dr.q_sample(tab, dr.norm_spec(fs2_mel, smin, smax).transpose(1, 2)[:, None], torch.tensor([K - 1]), qn)
+    fn = lambda a, b, c: dr.diffnet_forward(sd, cfg, a, b, c)
+    for i in reversed(range(K)):
+        x = dr.p_sample(tab, fn, x, torch.full((B,), i, dtype=torch.long), cond, bank[i])
+    mel = dr.denorm_spec(x[:, 0].transpose(1, 2), smin, smax) * (mel2ph > 0).float()[:, :, None]
+    e = rel_rmse(ret["mel_out"].cpu(), mel)
+    print("forward(infer=True) mel rel-RMSE vs oracle:", e)
+    assert e < 1e-3
+    assert float(ret["mel_out"][1, -5:].abs().max()) == 0.0
+
+
 def test_c3_full_size_properties():
     """BASELINE configs[2] shape: B=16, T=400, full DiffNet: batch independence + finite."""
     gd = make(specs.DIFFNET_BASE, 2025)
