@@ -90,7 +90,7 @@ template <int D>
 __global__ void __launch_bounds__(128) attention_tc_kernel(
     const float* __restrict__ q, int q_pitch, const float* __restrict__ k, int k_pitch,
     const float* __restrict__ v, int v_pitch, float* __restrict__ o, int o_pitch,
-    int Lq, int Lk, float qscale /* d^-0.5 * log2(e) */) {
+    int Lq, int Lk, float qscale /* d^-0.5 * log2(e) */, __half* __restrict__ phi, __half* __restrict__ plo) {
   using Cf = AtCfg<D>;
   extern __shared__ uint8_t at_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -293,7 +293,18 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(
     __syncthreads();      // every thread is done with S / O_blk / the K, V, P tiles of this block
   }
 
-  if (q0 + tid < Lq) {
+  if (q0 + tid < Lq && phi) {     // operand planes (fp16 hi/lo) instead of the fp32 tensor: the consumer is a plane-fed GEMM
+    const float inv = 1.f / l_run;
+    const long base = ((long)n * Lq + q0 + tid) * o_pitch + h * D;
+#pragma unroll
+    for (int c = 0; c < D; c += 8) {
+      uint4 hi, lo;
+      hi.x = at_split2(acc[c] * inv, acc[c + 1] * inv, lo.x); hi.y = at_split2(acc[c + 2] * inv, acc[c + 3] * inv, lo.y);
+      hi.z = at_split2(acc[c + 4] * inv, acc[c + 5] * inv, lo.z); hi.w = at_split2(acc[c + 6] * inv, acc[c + 7] * inv, lo.w);
+      *reinterpret_cast<uint4*>(phi + base + c) = hi;
+      *reinterpret_cast<uint4*>(plo + base + c) = lo;
+    }
+  } else if (q0 + tid < Lq) {
     const float inv = 1.f / l_run;
     float* op = o + ((long)n * Lq + q0 + tid) * o_pitch + h * D;
 #pragma unroll
@@ -309,7 +320,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(
 
 template <int D>
 void launch_at(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, float* o, int o_pitch,
-               int N, int heads, int Lq, int Lk, cudaStream_t st) {
+               int N, int heads, int Lq, int Lk, cudaStream_t st, __half* phi, __half* plo) {
   using Cf = AtCfg<D>;
   const size_t smem = Cf::TOTAL + 1024;
   static bool done[64] = {false};
@@ -321,18 +332,19 @@ void launch_at(const float* q, int q_pitch, const float* k, int k_pitch, const f
   }
   const float qscale = (1.0f / sqrtf((float)D)) * 1.4426950408889634f;     // dim_head ** -0.5 (attention.py:158), in log2 units
   dim3 grid(cdiv(Lq, AT_ROWS), heads, N);
-  attention_tc_kernel<D><<<grid, 128, smem, st>>>(q, q_pitch, k, k_pitch, v, v_pitch, o, o_pitch, Lq, Lk, qscale);
+  attention_tc_kernel<D><<<grid, 128, smem, st>>>(q, q_pitch, k, k_pitch, v, v_pitch, o, o_pitch, Lq, Lk, qscale, phi, plo);
 }
 
 }  // namespace
 
 // returns false when the head dim / alignment is not supported (caller uses the fp32 kernel)
 bool attention_tc(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch,
-                  float* o, int o_pitch, int N, int heads, int d, int Lq, int Lk, cudaStream_t st) {
+                  float* o, int o_pitch, int N, int heads, int d, int Lq, int Lk, cudaStream_t st, __half* phi, __half* plo) {
   if ((q_pitch | k_pitch | v_pitch | o_pitch) % 4 != 0) return false;
   if (((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
         reinterpret_cast<uintptr_t>(o)) & 15) != 0) return false;
-#define AGPT_ATC(D_) launch_at<D_>(q, q_pitch, k, k_pitch, v, v_pitch, o, o_pitch, N, heads, Lq, Lk, st)
+  if (phi && ((o_pitch % 8) != 0 || (d % 8) != 0 || ((reinterpret_cast<uintptr_t>(phi) | reinterpret_cast<uintptr_t>(plo)) & 15) != 0)) return false;
+#define AGPT_ATC(D_) launch_at<D_>(q, q_pitch, k, k_pitch, v, v_pitch, o, o_pitch, N, heads, Lq, Lk, st, phi, plo)
   switch (d) {
     case 8: AGPT_ATC(8); break;
     case 16: AGPT_ATC(16); break;

@@ -6,8 +6,15 @@
 #include "common.cuh"
 #include "models.h"
 #include "nn_kernels.h"
+#include <cuda_fp16.h>
 
 namespace agpt {
+
+// fp16 hi/lo operand-plane split of one value (tcconv7.cu consumes these planes through tensor maps)
+__device__ __forceinline__ void plane_split(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+  lo = __float2half_rn(v - __half2float(hi));
+}
 
 // ------------------------------------------------------------------ GroupNorm
 // One CTA per (sample, group): the group's slab -- HW rows x cpg contiguous channels -- is read ONCE into shared
@@ -34,7 +41,8 @@ __device__ __forceinline__ double gn_block_sum(double v, double* red) {
 template <int V>   // V = vector width in floats along the channel axis (cpg % V == 0)
 __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                               int HW, int C, int cpg, float eps, int silu, int cached) {
+                                                               int HW, int C, int cpg, float eps, int silu, int cached,
+                                                               __half* __restrict__ phi, __half* __restrict__ plo) {
   extern __shared__ __align__(16) float gn_cache[];
   __shared__ double red[GN_THREADS / 32];
   const int n = blockIdx.y, g = blockIdx.x;
@@ -77,6 +85,12 @@ __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(const float* __res
       if (silu) t = siluf_(t);
       o[k] = t;
     }
+    if (phi) {     // operand planes instead of the fp32 tensor (the consumer is a plane-fed GEMM)
+      const long base = ((long)n * HW + r) * C + g * cpg + c;
+#pragma unroll
+      for (int k = 0; k < V; ++k) plane_split(o[k], phi[base + k], plo[base + k]);
+      continue;
+    }
     if constexpr (V == 4) *reinterpret_cast<float4*>(yb + (long)r * C + c) = make_float4(o[0], o[1], o[2], o[3]);
     else if constexpr (V == 2) *reinterpret_cast<float2*>(yb + (long)r * C + c) = make_float2(o[0], o[1]);
     else yb[(long)r * C + c] = o[0];
@@ -84,7 +98,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(const float* __res
 }
 
 void groupnorm(const float* x, float* y, const float* gamma, const float* beta, int N, int HW, int C, int G,
-               float eps, bool silu, double* scratch, cudaStream_t st) {
+               float eps, bool silu, double* scratch, cudaStream_t st, __half* phi, __half* plo) {
   (void)scratch;
   AGPT_CHECK(C % G == 0 && C % 4 == 0, "GroupNorm: channels must be divisible by the group count and by 4");
   const int cpg = C / G;
@@ -102,9 +116,9 @@ void groupnorm(const float* x, float* y, const float* gamma, const float* beta, 
   }
   const dim3 grid(G, N);
   const int si = silu ? 1 : 0;
-  if (cpg % 4 == 0) gn_fused_kernel<4><<<grid, GN_THREADS, smem, st>>>(x, y, gamma, beta, HW, C, cpg, eps, si, cached);
-  else if (cpg % 2 == 0) gn_fused_kernel<2><<<grid, GN_THREADS, smem, st>>>(x, y, gamma, beta, HW, C, cpg, eps, si, cached);
-  else gn_fused_kernel<1><<<grid, GN_THREADS, smem, st>>>(x, y, gamma, beta, HW, C, cpg, eps, si, cached);
+  if (cpg % 4 == 0) gn_fused_kernel<4><<<grid, GN_THREADS, smem, st>>>(x, y, gamma, beta, HW, C, cpg, eps, si, cached, phi, plo);
+  else if (cpg % 2 == 0) gn_fused_kernel<2><<<grid, GN_THREADS, smem, st>>>(x, y, gamma, beta, HW, C, cpg, eps, si, cached, phi, plo);
+  else gn_fused_kernel<1><<<grid, GN_THREADS, smem, st>>>(x, y, gamma, beta, HW, C, cpg, eps, si, cached, phi, plo);
   count_launch(1);
   AGPT_CUDA(cudaGetLastError());
 }
@@ -112,7 +126,8 @@ size_t groupnorm_scratch_doubles(int N, int C) { (void)N; (void)C; return 16; }
 
 // ------------------------------------------------------------------ LayerNorm (one warp per row)
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, float* __restrict__ y, long rows, int C, float eps) {
+                                 const float* __restrict__ beta, float* __restrict__ y, long rows, int C, float eps,
+                                 __half* __restrict__ phi, __half* __restrict__ plo) {
   const long row = (long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -127,14 +142,18 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 #pragma unroll
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   const float rstd = rsqrtf(v / (float)C + eps);
+  if (phi) {       // operand planes instead of the fp32 tensor
+    for (int c = lane; c < C; c += 32) plane_split((xr[c] - mean) * rstd * gamma[c] + beta[c], phi[row * C + c], plo[row * C + c]);
+    return;
+  }
   float* yr = y + row * C;
   for (int c = lane; c < C; c += 32) yr[c] = (xr[c] - mean) * rstd * gamma[c] + beta[c];
 }
 
 void layernorm(const float* x, float* y, const float* gamma, const float* beta, long rows, int C, float eps,
-               cudaStream_t st) {
+               cudaStream_t st, __half* phi, __half* plo) {
   const int wpb = 8;
-  layernorm_kernel<<<(unsigned)cdivl(rows, wpb), wpb * 32, 0, st>>>(x, gamma, beta, y, rows, C, eps);
+  layernorm_kernel<<<(unsigned)cdivl(rows, wpb), wpb * 32, 0, st>>>(x, gamma, beta, y, rows, C, eps, phi, plo);
   count_launch(1);
   AGPT_CUDA(cudaGetLastError());
 }
@@ -226,12 +245,17 @@ __global__ void __launch_bounds__(128) attention_kernel(
 
 static int g_attn_tc = -1;
 void attention_set_tc(int on) { g_attn_tc = on; }
+bool attention_tc_enabled() {
+  if (g_attn_tc < 0) { const char* e = getenv("AGPT_ATTN_TC"); g_attn_tc = (e && e[0] == '0') ? 0 : 1; }
+  return g_attn_tc == 1;
+}
 
 void attention(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch,
-               float* o, int o_pitch, int N, int heads, int d, int Lq, int Lk, cudaStream_t st) {
+               float* o, int o_pitch, int N, int heads, int d, int Lq, int Lk, cudaStream_t st, __half* phi, __half* plo) {
   if (g_attn_tc < 0) { const char* e = getenv("AGPT_ATTN_TC"); g_attn_tc = (e && e[0] == '0') ? 0 : 1; }
   // tensor-core path (QK^T and PV on tcgen05, attention_tc.cu); the fp32 kernel below is the A/B reference
-  if (g_attn_tc == 1 && attention_tc(q, q_pitch, k, k_pitch, v, v_pitch, o, o_pitch, N, heads, d, Lq, Lk, st)) return;
+  if (g_attn_tc == 1 && attention_tc(q, q_pitch, k, k_pitch, v, v_pitch, o, o_pitch, N, heads, d, Lq, Lk, st, phi, plo)) return;
+  AGPT_CHECK(!phi, "operand-plane output needs the tcgen05 attention kernel (o must be given for the fp32 kernel)");
   const float scale = 1.0f / sqrtf((float)d);   // dim_head ** -0.5  (attention.py:158)
   dim3 grid(cdiv(Lq, 64), heads, N);
 #define AGPT_ATT(DH_) attention_kernel<DH_><<<grid, 128, 0, st>>>(q, q_pitch, k, k_pitch, v, v_pitch, o, o_pitch, Lq, Lk, scale)

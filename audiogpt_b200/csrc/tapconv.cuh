@@ -65,6 +65,9 @@ struct TapConvParams {
   // the halo of a 128-row tile stays 2*(strip_w+2)+2 rows whatever the image width is.  strips == 0: one virtual
   // grid [H][W + 1] per sample (one shared zero column), as the UNet's 10x78 maps use.
   int strips, strip_w;
+  // optional operand-plane copy of the GATE / GEGLU epilogue's output (fp16 hi/lo [L][pl_pitch], G == 1): the
+  // consumer (UNet ff2, a 4C-deep 1-tap GEMM) is then plane-fed; with out == nullptr the fp32 tensor is not written
+  __half* pl_hi; __half* pl_lo; int pl_pitch;
 };
 
 __host__ __device__ inline int tc_wv(const TapConvParams& P) { return P.Wreal > 0 ? (P.strips > 0 ? P.strip_w + 2 : P.Wreal + 1) : 0; }

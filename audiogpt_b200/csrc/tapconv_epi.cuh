@@ -114,7 +114,15 @@ __device__ __forceinline__ void epi_store_cv(const TapConvParams& P, int g, int 
         o.x = v.x * gelu_erf(v.y);
         o.y = v.z * gelu_erf(v.w);
       }
-      *reinterpret_cast<float2*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + (co >> 1)) = o;
+      if (P.out) *reinterpret_cast<float2*>(P.out + g * P.out_gstride + (long)p * P.out_pitch + (co >> 1)) = o;
+      if (P.pl_hi) {
+        const __half2 hh = __floats2half2_rn(fminf(fmaxf(o.x, -65504.f), 65504.f), fminf(fmaxf(o.y, -65504.f), 65504.f));
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(o.x - hf.x, o.y - hf.y);
+        const long off = (long)p * P.pl_pitch + (co >> 1);
+        *reinterpret_cast<__half2*>(P.pl_hi + off) = hh;
+        *reinterpret_cast<__half2*>(P.pl_lo + off) = ll;
+      }
       return;
     }
     case EPI_DIFFOUT: {
