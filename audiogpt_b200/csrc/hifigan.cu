@@ -123,7 +123,7 @@ struct AaFilter { float f[12]; };
 constexpr int AA_TT = 64;
 __global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                         const float* __restrict__ a, const float* __restrict__ inv_b,
-                                                        int L, int C, AaFilter F) {
+                                                        int L, int C, AaFilter F, __half* __restrict__ phi, __half* __restrict__ plo) {
   __shared__ float xs[AA_TT + 12][32];
   __shared__ float ss[2 * AA_TT + 10][32];
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -163,7 +163,14 @@ __global__ void __launch_bounds__(256) aa_snake_kernel(const float* __restrict__
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < 12; ++k) acc = fmaf(F.f[k], ss[2 * r + k][tx], acc);
-    yb[(long)t * C + c] = acc;
+    if (phi) {        // operand planes for the plane-fed conv that consumes this activation (no fp32 copy)
+      const __half hh = __float2half_rn(fminf(fmaxf(acc, -65504.f), 65504.f));
+      const long o = ((long)b * L + t) * C + c;
+      phi[o] = hh;
+      plo[o] = __float2half_rn(acc - __half2float(hh));
+    } else {
+      yb[(long)t * C + c] = acc;
+    }
   }
 }
 
@@ -475,7 +482,20 @@ struct Hifigan : Handle {
     float* S = sbuf.p;
     auto snake = [&](const float* src, float* dst, long Lr, int Cr, const SnakeW& w) {
       dim3 block(32, 8), grid(cdiv((int)Lr, AA_TT), cdiv(Cr, 32), B);
-      aa_snake_kernel<<<grid, block, 0, st>>>(src, dst, w.a.p, w.inv_b.p, (int)Lr, Cr, aaf);
+      aa_snake_kernel<<<grid, block, 0, st>>>(src, dst, w.a.p, w.inv_b.p, (int)Lr, Cr, aaf, nullptr, nullptr);
+      count_launch(1);
+      AGPT_CUDA(cudaGetLastError());
+    };
+    // BigVGAN in plane mode: the anti-aliased snake writes fp16 hi/lo operand planes and the conv that follows runs on
+    // the plane-fed kernel (fp32 result, no emitted planes: the next consumer is again a snake reading fp32)
+    static int allow_planes_b = -1;
+    if (allow_planes_b < 0) { const char* e = getenv("AGPT_PLANES"); allow_planes_b = (e && e[0] == '0') ? 0 : 1; }
+    const bool bplanes = big && allow_planes_b && planes_ok && !har && tc_enabled() && tc_get_version() >= 6;
+    Planes PS{nullptr, nullptr};
+    if (bplanes) PS = planes_of(pbuf[0], mx);
+    auto snake_planes = [&](const float* src, long Lr, int Cr, const SnakeW& w) {
+      dim3 block(32, 8), grid(cdiv((int)Lr, AA_TT), cdiv(Cr, 32), B);
+      aa_snake_kernel<<<grid, block, 0, st>>>(src, nullptr, w.a.p, w.inv_b.p, (int)Lr, Cr, aaf, PS.hi, PS.lo);
       count_launch(1);
       AGPT_CUDA(cudaGetLastError());
     };
@@ -493,7 +513,11 @@ struct Hifigan : Handle {
     for (int i = 0; i < cfg.num_upsamples; ++i) {
       const int u = cfg.upsample_rates[i];
       const int Co = C / 2;
-      {  // leaky_relu(0.1) -> ConvTranspose1d   (hifigan.py:153-154)
+      if (bplanes) {
+        make_planes(cur, PS.hi, PS.lo, (long)B * L * C, PRO_NONE, 0.f, st);
+        AGPT_CHECK(conv_planes(ups[i], B, L, C, 1, PS, X, u * Co, L * u * Co, nullptr, EPI_BIAS, nullptr, 1.f, 0, st),
+                   "plane-fed kernel rejected an upsample layer");
+      } else {  // leaky_relu(0.1) -> ConvTranspose1d   (hifigan.py:153-154)
         TapConvParams P = tapconv_params(ups[i], B, (int)L, 0, 1);
         P.in = cur; P.in_gstride = L * C; P.in_pitch = C;
         P.out = X; P.out_gstride = L * u * Co; P.out_pitch = u * Co;
@@ -518,6 +542,23 @@ struct Hifigan : Handle {
           const bool last = (n == nd - 1);
           float* dst = last ? acc : ((n & 1) ? R1 : R0);
           const float* conv_in = x;
+          if (bplanes) {
+            if (cfg.resblock_type == 1) {
+              snake_planes(x, L, C, rb.act[2 * n]);          // xt = a1(x)   (AMPBlock1.forward, models.py:75-76)
+              AGPT_CHECK(conv_planes(rb.c1[n], B, L, C, rb.dil[n], PS, A, C, gs, nullptr, EPI_BIAS, nullptr, 1.f, 0, st),
+                         "plane-fed kernel rejected an AMPBlock conv");
+              conv_in = A;
+            }
+            snake_planes(conv_in, L, C, rb.act[cfg.resblock_type == 1 ? 2 * n + 1 : n]);
+            const PackedConv& pc2 = (cfg.resblock_type == 1) ? rb.c2[n] : rb.c1[n];
+            const int d2 = (cfg.resblock_type == 1) ? 1 : rb.dil[n];
+            bool ok2;
+            if (last) ok2 = conv_planes(pc2, B, L, C, d2, PS, dst, C, gs, nullptr, EPI_ACC, x, inv_nk, j > 0 ? 1 : 0, st);
+            else ok2 = conv_planes(pc2, B, L, C, d2, PS, dst, C, gs, nullptr, EPI_RES, x, 1.f, 0, st);
+            AGPT_CHECK(ok2, "plane-fed kernel rejected an AMPBlock conv");
+            x = dst;
+            continue;
+          }
           if (cfg.resblock_type == 1) {
             if (big) snake(x, S, L, C, rb.act[2 * n]);      // xt = a1(x)   (AMPBlock1.forward, models.py:75-76)
             TapConvParams P = tapconv_params(rb.c1[n], B, (int)L, 0, rb.dil[n]);

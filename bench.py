@@ -622,6 +622,28 @@ def extra_metrics(dev):
     out["diffsinger_c3_launches_per_step"] = int(Lb.agpt_diffnet_launches_per_step(net._h))
     del net, gd
     torch.cuda.empty_cache()
+    # --- AutoencoderKL.decode ("next" row 8f-1): 4 latents 4x10x78 -> 4 mel images 1x80x624 (392.9 GFLOP per clip)
+    from audiogpt_b200.ldm.models.autoencoder import AutoencoderKL
+    cfgv = specs.VAE_TXT2AUDIO
+    vae = AutoencoderKL(ddconfig={k: v for k, v in cfgv.items() if k != "embed_dim"}, embed_dim=cfgv["embed_dim"])
+    vae.load_state_dict(specs.synth_vae_decoder(cfgv, 5150), strict=False)
+    vae = vae.eval().to(dev)
+    zz = specs.synth_tensor((4, 4, 10, 78), seed=3).to(dev)
+    for _ in range(2):
+        vae.decode(zz)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        ym = vae.decode(zz)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    msv = e0.elapsed_time(e1) / 3
+    out["vae_decode_ms_4clips"] = msv
+    out["vae_decode_clips_per_s"] = 4 / (msv * 1e-3)
+    out["vae_decode_tflops_algorithmic"] = 0.3929 * 4 / (msv * 1e-3)
+    out["vae_decode_finite"] = bool(torch.isfinite(ym).all().item())
+    del vae
+    torch.cuda.empty_cache()
     # --- BigVGAN ("next" row 8f-2: the vocoder Make-An-Audio actually dispatches), base 22 kHz / 80-band topology
     from audiogpt_b200.vocoder.bigvgan.models import BigVGAN
     hb = specs.BIGVGAN_BASE
