@@ -536,6 +536,72 @@ void ddim_update_tab(const float* x, const float* eps2, int single, const float*
   AGPT_CUDA(cudaGetLastError());
 }
 
+// The UNet's `out` conv (GN -> SiLU -> conv3x3 C -> 4, openaimodel.py:686,742) FUSED with classifier-free guidance
+// and the DDIM update (ddim.py:177-225): one warp per latent pixel computes the 4 output channels of BOTH guidance
+// halves (samples b and b + B) from the normalised activation hn [N][H*W][C] (lanes stride the channels, 128-bit
+// weight loads, warp-shuffle reduction), combines e = e_u + s (e_c - e_u) and writes x_prev / pred_x0 in place of
+// eps -- the epsilon tensor never exists in memory.  coef[*step] as in ddim_update_tab_kernel.
+__global__ void __launch_bounds__(256) conv_out_ddim_kernel(const float* __restrict__ hn, const float* __restrict__ w /*[9][C][4]*/,
+                                                             const float* __restrict__ bias, float* __restrict__ x /*[B][4][HW] in place*/,
+                                                             float* __restrict__ pred_x0, const float* __restrict__ coef,
+                                                             const int* __restrict__ step, int B, int H, int W, int C, int single) {
+  const int HW = H * W;
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  if (p >= HW) return;
+  const int ph = p / W, pw = p - ph * W;
+  const float* hu = hn + (long)b * HW * C;                 // unconditional half (or the only one)
+  const float* hc = hn + (long)(b + (single ? 0 : B)) * HW * C;
+  float au[4] = {0.f, 0.f, 0.f, 0.f}, ac[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int hh = ph + t / 3 - 1, ww = pw + t % 3 - 1;
+    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+    const long row = (long)(hh * W + ww) * C;
+    const float4* wt = reinterpret_cast<const float4*>(w) + (long)t * C;
+    for (int c = lane; c < C; c += 32) {
+      const float4 wv = __ldg(wt + c);
+      const float xu = __ldg(hu + row + c);
+      au[0] = fmaf(xu, wv.x, au[0]); au[1] = fmaf(xu, wv.y, au[1]); au[2] = fmaf(xu, wv.z, au[2]); au[3] = fmaf(xu, wv.w, au[3]);
+      if (!single) {
+        const float xc = __ldg(hc + row + c);
+        ac[0] = fmaf(xc, wv.x, ac[0]); ac[1] = fmaf(xc, wv.y, ac[1]); ac[2] = fmaf(xc, wv.z, ac[2]); ac[3] = fmaf(xc, wv.w, ac[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      au[k] += __shfl_xor_sync(0xffffffffu, au[k], o);
+      ac[k] += __shfl_xor_sync(0xffffffffu, ac[k], o);
+    }
+  }
+  if (lane < 4) {
+    const int k = lane;
+    const float* cf = coef + 6 * (long)(*step);
+    const float sqrt_at = cf[0], sqrt_aprev = cf[1], dir_coef = cf[2], sqrt_om = cf[4], s = cf[5];
+    const float sel_u = k == 0 ? au[0] : (k == 1 ? au[1] : (k == 2 ? au[2] : au[3]));
+    const float sel_c = k == 0 ? ac[0] : (k == 1 ? ac[1] : (k == 2 ? ac[2] : ac[3]));
+    const float eu = sel_u + bias[k];
+    float e = eu;
+    if (!single) { const float ec = sel_c + bias[k]; e = eu + s * (ec - eu); }
+    const long xi = ((long)b * 4 + k) * HW + p;
+    const float xv = x[xi];
+    const float p0 = (xv - sqrt_om * e) / sqrt_at;
+    x[xi] = sqrt_aprev * p0 + dir_coef * e + 0.f;
+    if (pred_x0) pred_x0[xi] = p0;
+  }
+}
+void conv_out_ddim(const float* hn, const float* w9c4, const float* bias4, float* x_io, float* pred_x0, const float* coef_dev,
+                   const int* step_dev, int B, int H, int W, int C, int single, cudaStream_t st) {
+  dim3 grid(cdiv(H * W, 8), B);
+  conv_out_ddim_kernel<<<grid, 256, 0, st>>>(hn, w9c4, bias4, x_io, pred_x0, coef_dev, step_dev, B, H, W, C, single);
+  count_launch(1);
+  AGPT_CUDA(cudaGetLastError());
+}
+
 void ddim_update(const float* x, const float* eps2, int single, float cfg_scale, float a_t, float a_prev,
                  float sigma_t, float sqrt_om, const float* noise, float temperature, int B, long n,
                  float* x_prev, float* pred_x0, cudaStream_t st) {

@@ -33,6 +33,8 @@ void select_row(const float* table, const int* step_dev, float* out, int ncols, 
 void step_inc(int* step_dev, cudaStream_t st);
 void ddim_update_tab(const float* x, const float* eps2, int single, const float* coef_dev, const int* step_dev, int B, long n,
                      float* x_prev, float* pred_x0, cudaStream_t st);
+void conv_out_ddim(const float* hn, const float* w9c4, const float* bias4, float* x_io, float* pred_x0, const float* coef_dev,
+                   const int* step_dev, int B, int H, int W, int C, int single, cudaStream_t st);
 void ddim_update(const float* x, const float* eps2, int single, float cfg_scale, float a_t, float a_prev,
                  float sigma_t, float sqrt_om, const float* noise, float temperature, int B, long n,
                  float* x_prev, float* pred_x0, cudaStream_t st);

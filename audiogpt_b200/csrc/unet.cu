@@ -46,6 +46,7 @@ struct Unet : Handle {
   PackedConv time0, time2, emb_all, ctx_kv_all, conv_in, conv_down, conv_up, conv_out;
   std::vector<PackedConv> down_convs, up_convs;
   DevBuf out_gn_g, out_gn_b;
+  DevBuf out_w9c4, out_b4;      // the `out` conv as [9][C][4] fp32 for the fused conv_out + CFG + DDIM-update kernel
   std::vector<ResW> res;
   std::vector<StW> st;
   std::vector<Block> in_blocks, out_blocks;
@@ -334,6 +335,8 @@ struct Unet : Handle {
   }
 
   // everything after the embedding: x [Nsrc][C][H][W] (sample n reads n % Nsrc) -> eps [N][Cout][H][W]
+  // eps == nullptr selects the FUSED tail of the sampling loop: out-conv + guidance + DDIM update in one kernel
+  // (conv_out_ddim: x_io = ddim_x updated in place, coefficients from coef_table[*step_ctr])
   void forward_core(const float* x, int Nsrc, const float* emb_out, int N, int H, int W, float* eps, cudaStream_t s) {
     float* x_cl = alloc((size_t)N * H * W * cin_pad);
     cf_to_cl_pad(x, x_cl, N, cfg.in_channels, cin_pad, H * W, s, Nsrc);
@@ -350,6 +353,11 @@ struct Unet : Handle {
     }
     float* hn = alloc((size_t)N * a.H * a.W * a.C);
     groupnorm(a.p, hn, out_gn_g.p, out_gn_b.p, N, a.H * a.W, a.C, 32, 1e-5f, true, reinterpret_cast<double*>(gn_scratch_f.p), s);
+    if (!eps) {
+      conv_out_ddim(hn, out_w9c4.p, out_b4.p, ddim_x.p, ddim_p0.p, coef_table.p, reinterpret_cast<const int*>(step_ctr.p),
+                    Nsrc, a.H, a.W, a.C, N == Nsrc ? 1 : 0, s);
+      return;
+    }
     {
       TapConvParams P = tapconv_params(conv_out, N, a.H * a.W, a.W, 1);
       P.in = hn; P.in_gstride = (long)a.H * a.W * a.C; P.in_pitch = a.C;
@@ -377,8 +385,14 @@ struct Unet : Handle {
     int* ctr = reinterpret_cast<int*>(step_ctr.p);
     select_row(emb_table.p, ctr, emb_cur.p, emb_total, s);
     emb_gstride = 0;
-    forward_core(ddim_x.p, B, emb_cur.p, N, H, W, ddim_eps.p, s);
-    ddim_update_tab(ddim_x.p, ddim_eps.p, N == B ? 1 : 0, coef_table.p, ctr, B, n, ddim_x.p, ddim_p0.p, s);
+    static int fuse_tail = -1;
+    if (fuse_tail < 0) { const char* e = getenv("AGPT_FUSE_DDIM"); fuse_tail = (e && e[0] == '0') ? 0 : 1; }
+    if (fuse_tail && out_w9c4.p) {
+      forward_core(ddim_x.p, B, emb_cur.p, N, H, W, nullptr, s);      // ... -> GN -> [out conv + CFG + x_prev update]
+    } else {
+      forward_core(ddim_x.p, B, emb_cur.p, N, H, W, ddim_eps.p, s);
+      ddim_update_tab(ddim_x.p, ddim_eps.p, N == B ? 1 : 0, coef_table.p, ctr, B, n, ddim_x.p, ddim_p0.p, s);
+    }
     step_inc(ctr, s);
   }
 };
@@ -524,7 +538,16 @@ Handle* unet_create(const agpt_unet_cfg* cfg, const float* const* W, int nW, int
   }
   u->final_ch = ch;
   { auto g = next(); auto b = next(); upload_vec(u->out_gn_g, g, ch); upload_vec(u->out_gn_b, b, ch); }
-  { auto w = next(); auto b = next(); pack_conv(u->conv_out, w, b, cfg->out_channels, ch, 9, true); }
+  { auto w = next(); auto b = next(); pack_conv(u->conv_out, w, b, cfg->out_channels, ch, 9, true);
+    if (cfg->out_channels == 4 && cfg->in_channels == 4) {
+      std::vector<float> w9((size_t)9 * ch * 4), b4(4);
+      for (int co = 0; co < 4; ++co) {
+        b4[co] = b[co];
+        for (int ci = 0; ci < ch; ++ci)
+          for (int k = 0; k < 9; ++k) w9[((size_t)k * ch + ci) * 4 + co] = w[((size_t)co * ch + ci) * 9 + k];
+      }
+      u->out_w9c4.upload(w9); u->out_b4.upload(b4);
+    } }
   AGPT_CHECK(idx == nW, "weight array count does not match the config");
 
   u->emb_total = emb_off; u->kv_total = kv_off;
