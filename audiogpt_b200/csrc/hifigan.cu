@@ -459,8 +459,11 @@ struct Hifigan : Handle {
   void forward(const float* mel, const float* har, int B, int T, float* wav, cudaStream_t st) {
     AGPT_CHECK(B >= 1 && T >= 1, "empty batch");
     {
+      // Measured on B200 (profiles/r2c_planes_microbench.txt, r2c_bench_planes.json): the plane-fed kernel wins on the
+      // latency-bound small GEMMs of the UNet but LOSES on this generator's big epilogue-bound layers (8 x 800 frames:
+      // 21.8 ms vs 18.5 ms) -- the extra plane stores cost more than the transform warps did.  Opt-in: AGPT_PLANES=1.
       static int allow_planes = -1;
-      if (allow_planes < 0) { const char* e = getenv("AGPT_PLANES"); allow_planes = (e && e[0] == '0') ? 0 : 1; }
+      if (allow_planes < 0) { const char* e = getenv("AGPT_PLANES"); allow_planes = (e && e[0] == '1') ? 1 : 0; }
       if (allow_planes && planes_ok && !har && cfg.activation == 0 && tc_enabled() && tc_get_version() >= 6) {
         forward_planes(mel, B, T, wav, st);
         return;
@@ -489,7 +492,7 @@ struct Hifigan : Handle {
     // BigVGAN in plane mode: the anti-aliased snake writes fp16 hi/lo operand planes and the conv that follows runs on
     // the plane-fed kernel (fp32 result, no emitted planes: the next consumer is again a snake reading fp32)
     static int allow_planes_b = -1;
-    if (allow_planes_b < 0) { const char* e = getenv("AGPT_PLANES"); allow_planes_b = (e && e[0] == '0') ? 0 : 1; }
+    if (allow_planes_b < 0) { const char* e = getenv("AGPT_PLANES"); allow_planes_b = (e && e[0] == '1') ? 1 : 0; }
     const bool bplanes = big && allow_planes_b && planes_ok && !har && tc_enabled() && tc_get_version() >= 6;
     Planes PS{nullptr, nullptr};
     if (bplanes) PS = planes_of(pbuf[0], mx);

@@ -140,9 +140,10 @@ void bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, i
         for (size_t i = 0; i < nout; ++i) {
           const float ref = a[i] > 0.f ? a[i] : 0.1f * a[i];
           const double got = (double)__half2float(ph[i]) + (double)__half2float(pl[i]);
-          pm = std::max(pm, std::fabs(got - (double)ref) / std::max(1e-3, std::fabs((double)ref)));
+          // hi + lo reproduces the value to 2^-21 relative, with the absolute floor 2^-24 of an fp16-subnormal lo part
+          pm = std::max(pm, std::fabs(got - (double)ref) / (std::fabs((double)ref) * 4.8e-7 + 6.0e-8));
         }
-        rel2[0] = std::max(rel2[0], pm > 1e-6 ? pm : 0.0);     // a plane error above 1e-6 relative fails the caller's gate
+        if (pm > 1.0) rel2[0] = std::max(rel2[0], pm);          // a plane outside that bound fails the caller's gate
       }
     }
   }

@@ -346,6 +346,25 @@ void softmax_rows(float* x, int pitch, long rows, int cols, float scale, cudaStr
   AGPT_CUDA(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------ GEGLU gate (attention.py:37-48) on operand planes
+// in [rows][2*Cg] with (a, gate) channel pairs interleaved (pack_conv_pairs) -> planes of a * gelu_erf(gate) [rows][Cg]
+__global__ void geglu_planes_kernel(const float* __restrict__ in, __half* __restrict__ phi, __half* __restrict__ plo, long n_pairs2) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs2; i += (long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);     // (a0, g0, a1, g1)
+    const float o0 = v.x * gelu_erf(v.y), o1 = v.z * gelu_erf(v.w);
+    const __half2 hh = __floats2half2_rn(fminf(fmaxf(o0, -65504.f), 65504.f), fminf(fmaxf(o1, -65504.f), 65504.f));
+    const float2 hf = __half22float2(hh);
+    reinterpret_cast<__half2*>(phi)[i] = hh;
+    reinterpret_cast<__half2*>(plo)[i] = __floats2half2_rn(o0 - hf.x, o1 - hf.y);
+  }
+}
+void geglu_planes(const float* in, __half* phi, __half* plo, long rows, int Cg, cudaStream_t st) {
+  const long n = rows * Cg / 2;
+  geglu_planes_kernel<<<(unsigned)std::min<long>(cdivl(n, 256), 8192), 256, 0, st>>>(in, phi, plo, n);
+  count_launch(1);
+  AGPT_CUDA(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------ timestep embedding (cos || sin)
 struct TParam { int t[256]; };
 __global__ void timestep_embed_kernel(float* __restrict__ out, const __grid_constant__ TParam tp, int dim) {

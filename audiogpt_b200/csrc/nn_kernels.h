@@ -21,6 +21,7 @@ void softmax_rows(float* x, int pitch, long rows, int cols, float scale, cudaStr
 bool attention_tc(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch,
                   float* o, int o_pitch, int N, int heads, int d, int Lq, int Lk, cudaStream_t st,
                   __half* phi = nullptr, __half* plo = nullptr);
+void geglu_planes(const float* in, __half* phi, __half* plo, long rows, int Cg, cudaStream_t st);
 void attention_set_tc(int on);
 bool attention_tc_enabled();   // 1 (default) tcgen05, 0 fp32 kernel, -1 environment (AGPT_ATTN_TC)
 void timestep_embedding(float* out, const int* t_host, int N, int dim, cudaStream_t st);

@@ -181,6 +181,7 @@ struct Unet : Handle {
     AGPT_CHECK(linear_planes(t.proj_in, pa, t.ch, h, C, rows, EPI_BIAS, nullptr, 0, nullptr, s), "plane-fed GEMM rejected proj_in");
     float* a = alloc(rows * C);
     float* qkv = alloc(rows * 3 * C);
+    float* ff8 = alloc(rows * 8 * C);
     for (size_t bi = 0; bi < t.blocks.size(); ++bi) {
       const XfBlockW& b = t.blocks[bi];
       const bool last = bi + 1 == t.blocks.size();
@@ -196,9 +197,17 @@ struct Unet : Handle {
                 HW, ctxS, s, pt.hi, pt.lo);
       float* h3 = alloc(rows * C);
       AGPT_CHECK(linear_planes(b.out2, pt, C, h3, C, rows, EPI_RES, h2, C, nullptr, s), "plane-fed GEMM rejected attn2.to_out");
-      // GEGLU feed-forward: ff1 keeps the fp32-input kernel (its gate epilogue), writing ONLY the planes of u * gelu(g)
-      layernorm(h3, a, b.ln3_g.p, b.ln3_b.p, rows, C, 1e-5f, s);
-      {
+      // GEGLU feed-forward (attention.py:37-64): ff1 on the plane-fed kernel writes the (a, gate) pairs in fp32, one
+      // light pass turns them into the planes of a * gelu(gate) that ff2 consumes (AGPT_GEGLU_TC5=1: round-1 path,
+      // the gate fused in the one-tile-per-CTA kernel's epilogue)
+      static int geglu_tc5 = -1;
+      if (geglu_tc5 < 0) { const char* e = getenv("AGPT_GEGLU_TC5"); geglu_tc5 = (e && e[0] == '1') ? 1 : 0; }
+      if (!geglu_tc5) {
+        layernorm(h3, nullptr, b.ln3_g.p, b.ln3_b.p, rows, C, 1e-5f, s, pa.hi, pa.lo);
+        AGPT_CHECK(linear_planes(b.ff1, pa, C, ff8, 8 * C, rows, EPI_BIAS, nullptr, 0, nullptr, s), "plane-fed GEMM rejected ff.net.0.proj");
+        geglu_planes(ff8, pf.hi, pf.lo, rows, 4 * C, s);
+      } else {
+        layernorm(h3, a, b.ln3_g.p, b.ln3_b.p, rows, C, 1e-5f, s);
         TapConvParams P = tapconv_params(b.ff1, 1, (int)rows, 0, 1);
         P.in = a; P.in_pitch = C;
         P.out = nullptr; P.out_pitch = 4 * C;
@@ -312,7 +321,7 @@ struct Unet : Handle {
     size_t maxc = 0;
     for (auto& r : res) maxc = std::max(maxc, (size_t)std::max(r.cin, r.cout));
     per_res = 5 * hw * maxc;
-    per_st = 16 * hw * maxc;
+    per_st = 26 * hw * maxc;
     const size_t nblocks = in_blocks.size() + out_blocks.size() + 1;
     return (size_t)N * (nblocks * (2 * per_res + per_st + 3 * hw * maxc * 3)) + (1 << 20);
   }

@@ -23,7 +23,7 @@ def build(cfg, seed=5150):
                           "loss.logvar": torch.zeros(())})
     missing = m.load_state_dict(sd_ckpt, strict=False)
     assert not missing.missing_keys and set(missing.unexpected_keys) == {"encoder.conv_in.weight", "quant_conv.weight", "loss.logvar"}
-    assert list(m.state_dict().keys()) == list(specs.vae_decoder_param_shapes(cfg).keys())
+    assert set(m.state_dict().keys()) == set(specs.vae_decoder_param_shapes(cfg).keys())
     return m.eval().to("cuda"), sd
 
 
