@@ -18,7 +18,7 @@ for G, Ln, Cin, Cout, K, dil, Wr in SHAPES:
     for epi_res in (0, 1):
         rel = (C.c_double * 2)()
         _lib.check(L.agpt_check_tapconv(G, Ln, Cin, Cout, K, dil, Wr, epi_res, C.c_double(1.0), C.c_double(1.0), rel))
-        ok = rel[0] < 2e-5
+        ok = rel[0] < 2e-4 and rel[1] < 2e-5
         bad += 0 if ok else 1
         print(f"v{ver} G={G} L={Ln} {Cin}->{Cout} k={K} dil={dil} W={Wr} res={epi_res}: max/rms {rel[0]:.2e} rms/rms {rel[1]:.2e} {'ok' if ok else 'FAIL'}", flush=True)
 sys.exit(1 if bad else 0)
