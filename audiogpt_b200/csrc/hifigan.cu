@@ -319,6 +319,8 @@ struct ResBlockW {
   int ks = 0;
   std::vector<int> dil;
   std::vector<PackedConv> c1, c2;  // c2 empty for ResBlock2
+  std::vector<PackedConv> c1g, c2g;  // time-grouped images of the dilation-1 convs of narrow stages (pack_conv_grouped)
+  std::vector<int> g1, g2;           // their group factor (0: not grouped)
   std::vector<SnakeW> act;          // BigVGAN: one anti-aliased snake per conv (AMPBlock1: 2 per pair)
 };
 
@@ -564,9 +566,10 @@ struct Hifigan : Handle {
           }
           if (cfg.resblock_type == 1) {
             if (big) snake(x, S, L, C, rb.act[2 * n]);      // xt = a1(x)   (AMPBlock1.forward, models.py:75-76)
-            TapConvParams P = tapconv_params(rb.c1[n], B, (int)L, 0, rb.dil[n]);
-            P.in = big ? S : x; P.in_gstride = gs; P.in_pitch = C;
-            P.out = A; P.out_gstride = gs; P.out_pitch = C;
+            const int gq = (rb.g1[n] && L % rb.g1[n] == 0) ? rb.g1[n] : 1;      // time-grouped view [L/g][g*C] of the same memory
+            TapConvParams P = gq > 1 ? tapconv_params(rb.c1g[n], B, (int)(L / gq), 0, 1) : tapconv_params(rb.c1[n], B, (int)L, 0, rb.dil[n]);
+            P.in = big ? S : x; P.in_gstride = gs; P.in_pitch = gq * C;
+            P.out = A; P.out_gstride = gs; P.out_pitch = gq * C;
             P.pro = big ? PRO_NONE : PRO_LRELU; P.slope = 0.1f; P.epi = EPI_BIAS;
             tapconv_launch(P, st);
             conv_in = A;
@@ -575,12 +578,15 @@ struct Hifigan : Handle {
             snake(conv_in, S, L, C, rb.act[cfg.resblock_type == 1 ? 2 * n + 1 : n]);
             conv_in = S;
           }
-          const PackedConv& pc = (cfg.resblock_type == 1) ? rb.c2[n] : rb.c1[n];
-          TapConvParams P = tapconv_params(pc, B, (int)L, 0, (cfg.resblock_type == 1) ? 1 : rb.dil[n]);
-          P.in = conv_in; P.in_gstride = gs; P.in_pitch = C;
-          P.out = dst; P.out_gstride = gs; P.out_pitch = C;
+          const bool t1 = cfg.resblock_type == 1;
+          const int gq0 = t1 ? rb.g2[n] : rb.g1[n];
+          const int gq = (gq0 && L % gq0 == 0) ? gq0 : 1;
+          const PackedConv& pc = gq > 1 ? (t1 ? rb.c2g[n] : rb.c1g[n]) : (t1 ? rb.c2[n] : rb.c1[n]);
+          TapConvParams P = gq > 1 ? tapconv_params(pc, B, (int)(L / gq), 0, 1) : tapconv_params(pc, B, (int)L, 0, t1 ? 1 : rb.dil[n]);
+          P.in = conv_in; P.in_gstride = gs; P.in_pitch = gq * C;
+          P.out = dst; P.out_gstride = gs; P.out_pitch = gq * C;
           P.pro = big ? PRO_NONE : PRO_LRELU; P.slope = 0.1f;
-          P.res = x; P.res_gstride = gs; P.res_pitch = C;
+          P.res = x; P.res_gstride = gs; P.res_pitch = gq * C;
           if (last) { P.epi = EPI_ACC; P.scale = inv_nk; P.accumulate = (j > 0); }
           else P.epi = EPI_RES;
           tapconv_launch(P, st);
@@ -649,11 +655,30 @@ Handle* hifigan_create(const agpt_hifigan_cfg* cfg, const float* const* W, int n
       AGPT_CHECK(rb.ks % 2 == 1 && rb.ks <= kMaxTaps, "resblock kernel size must be odd and <= 11");
       const int nd = cfg->resblock_num_dilations[j];
       rb.dil.assign(cfg->resblock_dilations[j], cfg->resblock_dilations[j] + nd);
-      rb.c1.resize(nd);
-      for (int n = 0; n < nd; ++n) { const float* w = next(); const float* b = next(); pack_conv(rb.c1[n], w, b, C, C, rb.ks, false); }
+      // narrow stages: dilation-1 convs with k >= 7 also get a time-grouped image (N = 128 per MMA instead of C)
+      static int allow_group = -1;
+      if (allow_group < 0) { const char* e = getenv("AGPT_TIME_GROUP"); allow_group = (e && e[0] == '0') ? 0 : 1; }
+      auto group_of = [&](int dil) {
+        if (!allow_group || cfg->activation != 0 || dil != 1 || rb.ks < 7) return 0;
+        if (C == 32) return 4;
+        if (C == 64 && rb.ks >= 11) return 2;
+        return 0;
+      };
+      rb.c1.resize(nd); rb.c1g.resize(nd); rb.g1.assign(nd, 0);
+      for (int n = 0; n < nd; ++n) {
+        const float* w = next(); const float* b = next();
+        pack_conv(rb.c1[n], w, b, C, C, rb.ks, false);
+        rb.g1[n] = group_of(rb.dil[n]);
+        if (rb.g1[n]) pack_conv_grouped(rb.c1g[n], w, b, C, rb.ks, rb.g1[n]);
+      }
       if (cfg->resblock_type == 1) {
-        rb.c2.resize(nd);
-        for (int n = 0; n < nd; ++n) { const float* w = next(); const float* b = next(); pack_conv(rb.c2[n], w, b, C, C, rb.ks, false); }
+        rb.c2.resize(nd); rb.c2g.resize(nd); rb.g2.assign(nd, 0);
+        for (int n = 0; n < nd; ++n) {
+          const float* w = next(); const float* b = next();
+          pack_conv(rb.c2[n], w, b, C, C, rb.ks, false);
+          rb.g2[n] = group_of(1);
+          if (rb.g2[n]) pack_conv_grouped(rb.c2g[n], w, b, C, rb.ks, rb.g2[n]);
+        }
       }
       if (cfg->activation != 0) {
         rb.act.resize(cfg->resblock_type == 1 ? 2 * nd : nd);

@@ -205,6 +205,37 @@ inline void pack_conv(PackedConv& pc, const float* w, const float* b, int Cout, 
   pc.b.upload(hb);
 }
 
+// Conv1d (dilation 1, "same" padding) on g CONSECUTIVE TIME STEPS AT ONCE: the [L][C] tensor is read as [L/g][g*C]
+// (the same memory), so a k-tap conv over C channels becomes a conv over g*C channels with block-Toeplitz weights
+//   W'[s][(i, ci)][(j, co)] = w[co][ci][g*s + i - j + c],   c = (k-1)/2,  s = floor((j + t - c) / g)
+// over super-taps s.  Narrow layers (C = 32 / 64) are bound by the NUMBER of tcgen05.mma instructions -- each one
+// re-reads its 128-row A slice whatever N is (profiles/r1e_findings.md) -- and this raises N per instruction from C to
+// g*C = 128: k = 11, C = 32, g = 4 needs 5 super-taps x 8 k-steps per 512 time steps instead of 11 x 2 per 128
+// (2.2x fewer MMAs); the zero blocks of W' cost 1.45x the algorithmic MACs, which the tensor pipe has to spare.
+inline void pack_conv_grouped(PackedConv& pc, const float* w, const float* b, int C, int K, int g) {
+  const int c = (K - 1) / 2;
+  auto fdiv = [](int a, int d) { return a >= 0 ? a / d : -((-a + d - 1) / d); };
+  const int smin = fdiv(-c, g), smax = fdiv(g - 1 + K - 1 - c, g);
+  const int nt = smax - smin + 1;
+  AGPT_CHECK(nt <= kMaxTaps, "grouped conv: too many super-taps");
+  const int Cg = g * C;
+  std::vector<float> wg((size_t)Cg * Cg * nt, 0.f), bg(Cg, 0.f);
+  for (int j = 0; j < g; ++j)
+    for (int co = 0; co < C; ++co) {
+      if (b) bg[j * C + co] = b[co];
+      for (int i = 0; i < g; ++i)
+        for (int ci = 0; ci < C; ++ci)
+          for (int s = smin; s <= smax; ++s) {
+            const int t = g * s + i - j + c;
+            if (t < 0 || t >= K) continue;
+            wg[((size_t)(j * C + co) * Cg + (i * C + ci)) * nt + (s - smin)] = w[((size_t)co * C + ci) * K + t];
+          }
+    }
+  pack_conv(pc, wg.data(), b ? bg.data() : nullptr, Cg, Cg, nt, false);
+  for (int t = 0; t < nt; ++t) pc.tap_off_1d[t] = smin + t;
+  pc.useful = (float)K / (float)(nt * g);
+}
+
 // Same, but output channels interleaved (co -> 2*(co % half) + co / half): used where the
 // epilogue consumes (first-half, second-half) channel pairs (DiffNet gate/filter, GEGLU).
 inline void pack_conv_pairs(PackedConv& pc, const float* w, const float* b, int Cout, int Cin, int K) {
