@@ -84,6 +84,9 @@ struct AtCfg {
   static constexpr uint32_t P_BYTES = 2u * AT_ROWS * 128;
   static constexpr uint32_t TOTAL = Q_BYTES + K_BYTES + V_BYTES + P_BYTES;
   static constexpr uint32_t TMEM_COLS = (AT_BK + DP <= 128) ? 128 : 256;
+  static constexpr bool PF = D <= 64;      // software-prefetch the next K / V block into registers (register budget: d <= 64)
+  static constexpr int KIT = (AT_BK * NCH * 8 + 127) / 128;   // K items (8 channels of one key) per thread
+  static constexpr int VIT = (VROWS / 4 + 1) / 2;             // V channel quads per thread
 };
 
 template <int D>
@@ -156,50 +159,74 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(
   const int nblk = (Lk + AT_BK - 1) / AT_BK;
   uint32_t phase = 0;
 
+  // K items: (key row, 8-channel chunk) -> two float4; V items: (key, channel quad) -> one float4
+  float4 kreg[Cf::KIT][2];
+  float4 vreg[Cf::VIT];
+  constexpr int CH8 = Cf::NCH * 8;
+  auto load_kv = [&](int j0) {
+#pragma unroll
+    for (int u = 0; u < Cf::KIT; ++u) {
+      const int it = tid + 128 * u;
+      const int row = it / CH8, c8 = it - row * CH8;
+      const int ch = c8 * 8;
+      kreg[u][0] = make_float4(0.f, 0.f, 0.f, 0.f); kreg[u][1] = kreg[u][0];
+      if (it < AT_BK * CH8 && j0 + row < Lk && ch < D) {
+        const float* p = kb + (long)(j0 + row) * k_pitch + ch;
+        kreg[u][0] = *reinterpret_cast<const float4*>(p);
+        kreg[u][1] = *reinterpret_cast<const float4*>(p + 4);
+      }
+    }
+    const int key = tid & 63, half = tid >> 6;          // two groups of 64 threads split the channel quads
+    const bool kok = j0 + key < Lk;
+    const float* p = vb + (long)(j0 + key) * v_pitch;
+#pragma unroll
+    for (int u = 0; u < Cf::VIT; ++u) {
+      const int ch = (half + 2 * u) * 4;
+      vreg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kok && ch < D) vreg[u] = *reinterpret_cast<const float4*>(p + ch);
+    }
+  };
+  auto store_kv = [&]() {
+    // K -> K-major hi/lo tiles (rows = keys)
+#pragma unroll
+    for (int u = 0; u < Cf::KIT; ++u) {
+      const int it = tid + 128 * u;
+      if (it >= AT_BK * CH8) continue;
+      const int row = it / CH8, c8 = it - row * CH8;
+      const float4 a = kreg[u][0], b = kreg[u][1];
+      uint4 hi, lo;
+      hi.x = at_split2(a.x, a.y, lo.x); hi.y = at_split2(a.z, a.w, lo.y);
+      hi.z = at_split2(b.x, b.y, lo.z); hi.w = at_split2(b.z, b.w, lo.w);
+      const uint32_t off = (uint32_t)(c8 >> 3) * (AT_BK * 128) + sw128(row, c8 & 7);
+      *reinterpret_cast<uint4*>(k_hi + off) = hi;
+      *reinterpret_cast<uint4*>(k_lo + off) = lo;
+    }
+    // V -> transposed tiles [channel rows][64 keys]; lanes take consecutive keys (conflict-free columns)
+    const int key = tid & 63, half = tid >> 6;
+#pragma unroll
+    for (int u = 0; u < Cf::VIT; ++u) {
+      const int c4 = half + 2 * u;
+      if (c4 >= Cf::VROWS / 4) continue;
+      const int ch = c4 * 4;
+      const float vals[4] = {vreg[u].x, vreg[u].y, vreg[u].z, vreg[u].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __half hh = __float2half_rn(vals[i]);
+        const __half ll = __float2half_rn(vals[i] - __half2float(hh));
+        const uint32_t off = sw128(ch + i, key >> 3) + (uint32_t)(key & 7) * 2u;
+        *reinterpret_cast<__half*>(v_hi + off) = hh;
+        *reinterpret_cast<__half*>(v_lo + off) = ll;
+      }
+    }
+  };
+
   for (int blk = 0; blk < nblk; ++blk) {
     const int j0 = blk * AT_BK;
-    // ---- K block -> K-major hi/lo tiles (rows = keys)
-    {
-      constexpr int CH8 = Cf::NCH * 8;
-      for (int it = tid; it < AT_BK * CH8; it += 128) {
-        const int row = it / CH8, c8 = it - row * CH8;
-        const int ch = c8 * 8;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-        if (j0 + row < Lk && ch < D) {
-          const float* p = kb + (long)(j0 + row) * k_pitch + ch;
-          a = *reinterpret_cast<const float4*>(p);
-          b = *reinterpret_cast<const float4*>(p + 4);
-        }
-        uint4 hi, lo;
-        hi.x = at_split2(a.x, a.y, lo.x); hi.y = at_split2(a.z, a.w, lo.y);
-        hi.z = at_split2(b.x, b.y, lo.z); hi.w = at_split2(b.z, b.w, lo.w);
-        const uint32_t off = (uint32_t)(c8 >> 3) * (AT_BK * 128) + sw128(row, c8 & 7);
-        *reinterpret_cast<uint4*>(k_hi + off) = hi;
-        *reinterpret_cast<uint4*>(k_lo + off) = lo;
-      }
-    }
-    // ---- V block -> transposed tiles [channel rows][64 keys]; lanes take consecutive keys (conflict-free columns)
-    {
-      const int key = tid & 63, half = tid >> 6;          // two groups of 64 threads split the channel quads
-      const bool kok = j0 + key < Lk;
-      const float* p = vb + (long)(j0 + key) * v_pitch;
-      constexpr int NQ = Cf::VROWS / 4;
-      for (int c4 = half; c4 < NQ; c4 += 2) {
-        const int ch = c4 * 4;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kok && ch < D) a = *reinterpret_cast<const float4*>(p + ch);
-        const float vals[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const __half hh = __float2half_rn(vals[i]);
-          const __half ll = __float2half_rn(vals[i] - __half2float(hh));
-          const int row = ch + i;
-          const uint32_t off = sw128(row, key >> 3) + (uint32_t)(key & 7) * 2u;
-          *reinterpret_cast<__half*>(v_hi + off) = hh;
-          *reinterpret_cast<__half*>(v_lo + off) = ll;
-        }
-      }
-    }
+    // ---- K / V block of this iteration: from the prefetch registers (loaded one block ahead, so that the global
+    //      latency hides behind the previous block's MMA / softmax phases) or straight from global memory
+    if (!Cf::PF || blk == 0) load_kv(j0);
+    store_kv();
+    if (Cf::PF && blk + 1 < nblk) load_kv(j0 + AT_BK);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
