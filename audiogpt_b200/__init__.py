@@ -8,6 +8,9 @@ Drop-in classes (same names / signatures / state-dict layouts as the reference):
     audiogpt_b200.modules.diff.shallow_diffusion_tts.GaussianDiffusion
     audiogpt_b200.ldm.modules.diffusionmodules.openaimodel.UNetModel
     audiogpt_b200.ldm.models.diffusion.ddim.DDIMSampler
+    audiogpt_b200.ldm.models.autoencoder.AutoencoderKL          (decode side; not installed over the reference class)
+    audiogpt_b200.modules.fastspeech.pe.PitchExtractor
+    audiogpt_b200.vocoder.bigvgan.models.BigVGAN / VocoderBigVGAN
 
 All arithmetic lives in libagpt_b200.so (audiogpt_b200/csrc, C ABI in include/agpt_b200.h).
 There is no CPU fallback.
@@ -25,6 +28,7 @@ _INSTALL_MAP = {
                                                  ["UNetModel"]),
     "ldm.models.diffusion.ddim": ("audiogpt_b200.ldm.models.diffusion.ddim", ["DDIMSampler"]),
     "vocoder.bigvgan.models": ("audiogpt_b200.vocoder.bigvgan.models", ["BigVGAN", "VocoderBigVGAN"]),
+    "modules.fastspeech.pe": ("audiogpt_b200.modules.fastspeech.pe", ["PitchExtractor"]),
 }
 
 

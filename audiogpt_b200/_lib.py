@@ -55,6 +55,11 @@ class VaeCfg(C.Structure):
                 ("attn_at_level", C.c_int * AGPT_MAX_LEVELS)]
 
 
+class PeCfg(C.Structure):
+    _fields_ = [("n_mel_bins", C.c_int), ("hidden_size", C.c_int), ("conv_layers", C.c_int),
+                ("predictor_hidden", C.c_int), ("predictor_layers", C.c_int), ("predictor_kernel", C.c_int)]
+
+
 _lock = threading.Lock()
 _lib = None
 

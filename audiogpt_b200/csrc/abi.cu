@@ -228,6 +228,22 @@ int agpt_vae_decode(agpt_handle h, const float* z, int B, int H, int W, float* o
   });
 }
 
+int agpt_pe_create(const agpt_pe_cfg* cfg, const float* const* host_weights, int n_weights, int device, agpt_handle* out) {
+  return guarded([&] {
+    AGPT_CHECK(cfg && host_weights && out, "null argument");
+    *out = reinterpret_cast<agpt_handle>(pe_create(cfg, host_weights, n_weights, device));
+  });
+}
+
+int agpt_pe_forward(agpt_handle h, const float* mel, int B, int T, float* pitch_pred, float* f0_denorm, int use_uv,
+                    int pitch_norm, float f0_mean, float f0_std, void* stream) {
+  return guarded([&] {
+    AGPT_CHECK(mel && pitch_pred && f0_denorm, "null argument");
+    pe_forward(as(h, kMagicPe, "pitch extractor"), mel, B, T, pitch_pred, f0_denorm, use_uv, pitch_norm, f0_mean, f0_std,
+               (cudaStream_t)stream);
+  });
+}
+
 int agpt_bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, int epi_res, int use_tc, int reps,
                        int check, double* out3, double* dbg8_or_null) {
   return guarded([&] { bench_tapconv(G, L, Cin, Cout, K, dil, Wreal, epi_res, use_tc, reps, check, out3, dbg8_or_null); });

@@ -88,6 +88,7 @@ constexpr uint32_t kMagicHifigan = 0x48494649;  // 'HIFI'
 constexpr uint32_t kMagicDiffnet = 0x44494646;  // 'DIFF'
 constexpr uint32_t kMagicUnet = 0x554e4554;     // 'UNET'
 constexpr uint32_t kMagicVae = 0x56414544;      // 'VAED'
+constexpr uint32_t kMagicPe = 0x50495443;       // 'PITC'
 
 // ---- small device functions --------------------------------------------------
 __device__ __forceinline__ float lrelu(float x, float a) { return x > 0.f ? x : a * x; }

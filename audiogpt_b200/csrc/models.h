@@ -41,6 +41,10 @@ long unet_launches_per_step(Handle* h);
 Handle* vae_create(const agpt_vae_cfg* cfg, const float* const* W, int nW, int device);
 void vae_decode(Handle* h, const float* z, int B, int H, int W, float* out, cudaStream_t st);
 
+Handle* pe_create(const agpt_pe_cfg* cfg, const float* const* W, int nW, int device);
+void pe_forward(Handle* h, const float* mel, int B, int T, float* pitch_pred, float* f0, int use_uv, int norm_mode,
+                float f0_mean, float f0_std, cudaStream_t st);
+
 void bench_tapconv(int G, int L, int Cin, int Cout, int K, int dil, int Wreal, int epi_res, int use_tc, int reps,
                    int check, double* out, double* dbg_avg, double x_scale = 1.0, double w_spread = 1.0, double* rel2 = nullptr);
 

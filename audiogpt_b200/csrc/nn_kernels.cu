@@ -41,8 +41,9 @@ __device__ __forceinline__ double gn_block_sum(double v, double* red) {
 template <int V>   // V = vector width in floats along the channel axis (cpg % V == 0)
 __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                               int HW, int C, int cpg, float eps, int silu, int cached,
-                                                               __half* __restrict__ phi, __half* __restrict__ plo) {
+                                                               int HW, int C, int cpg, float eps, int silu /* 0 none, 1 SiLU, 2 ReLU */, int cached,
+                                                               __half* __restrict__ phi, __half* __restrict__ plo,
+                                                               const float* __restrict__ res /* added after the activation, or null */) {
   extern __shared__ __align__(16) float gn_cache[];
   __shared__ double red[GN_THREADS / 32];
   const int n = blockIdx.y, g = blockIdx.x;
@@ -82,7 +83,9 @@ __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(const float* __res
     for (int k = 0; k < V; ++k) {
       const float xv = cached ? gn_cache[k * nvec + i] : __ldg(xb + (long)r * C + c + k);
       float t = (xv - mean) * rstd * __ldg(gamma + g * cpg + c + k) + __ldg(beta + g * cpg + c + k);
-      if (silu) t = siluf_(t);
+      if (silu == 1) t = siluf_(t);
+      else if (silu == 2) t = fmaxf(t, 0.f);
+      if (res) t += __ldg(res + ((long)n * HW + r) * C + g * cpg + c + k);
       o[k] = t;
     }
     if (phi) {     // operand planes instead of the fp32 tensor (the consumer is a plane-fed GEMM)
@@ -100,6 +103,12 @@ __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(const float* __res
 void groupnorm(const float* x, float* y, const float* gamma, const float* beta, int N, int HW, int C, int G,
                float eps, bool silu, double* scratch, cudaStream_t st, __half* phi, __half* plo) {
   (void)scratch;
+  groupnorm_ex(x, y, gamma, beta, N, HW, C, G, eps, silu ? 1 : 0, nullptr, st, phi, plo);
+}
+
+// act: 0 none, 1 SiLU, 2 ReLU; res (optional, same layout as y) is added after the activation (ConvStacks' x + f(x))
+void groupnorm_ex(const float* x, float* y, const float* gamma, const float* beta, int N, int HW, int C, int G,
+                  float eps, int act, const float* res, cudaStream_t st, __half* phi, __half* plo) {
   AGPT_CHECK(C % G == 0 && C % 4 == 0, "GroupNorm: channels must be divisible by the group count and by 4");
   const int cpg = C / G;
   const long slab = (long)HW * cpg;
@@ -115,10 +124,10 @@ void groupnorm(const float* x, float* y, const float* gamma, const float* beta, 
     attr_done_dev[dev & 63] = true;
   }
   const dim3 grid(G, N);
-  const int si = silu ? 1 : 0;
-  if (cpg % 4 == 0) gn_fused_kernel<4><<<grid, GN_THREADS, smem, st>>>(x, y, gamma, beta, HW, C, cpg, eps, si, cached, phi, plo);
-  else if (cpg % 2 == 0) gn_fused_kernel<2><<<grid, GN_THREADS, smem, st>>>(x, y, gamma, beta, HW, C, cpg, eps, si, cached, phi, plo);
-  else gn_fused_kernel<1><<<grid, GN_THREADS, smem, st>>>(x, y, gamma, beta, HW, C, cpg, eps, si, cached, phi, plo);
+  const int si = act;
+  if (cpg % 4 == 0) gn_fused_kernel<4><<<grid, GN_THREADS, smem, st>>>(x, y, gamma, beta, HW, C, cpg, eps, si, cached, phi, plo, res);
+  else if (cpg % 2 == 0) gn_fused_kernel<2><<<grid, GN_THREADS, smem, st>>>(x, y, gamma, beta, HW, C, cpg, eps, si, cached, phi, plo, res);
+  else gn_fused_kernel<1><<<grid, GN_THREADS, smem, st>>>(x, y, gamma, beta, HW, C, cpg, eps, si, cached, phi, plo, res);
   count_launch(1);
   AGPT_CUDA(cudaGetLastError());
 }

@@ -7,6 +7,8 @@ namespace agpt {
 
 void groupnorm(const float* x, float* y, const float* gamma, const float* beta, int N, int HW, int C, int G,
                float eps, bool silu, double* scratch, cudaStream_t st, __half* phi = nullptr, __half* plo = nullptr);
+void groupnorm_ex(const float* x, float* y, const float* gamma, const float* beta, int N, int HW, int C, int G,
+                  float eps, int act, const float* res, cudaStream_t st, __half* phi = nullptr, __half* plo = nullptr);
 size_t groupnorm_scratch_doubles(int N, int C);
 // phi / plo given: the result is written as fp16 hi/lo operand planes [rows][C] INSTEAD of the fp32 tensor y
 void layernorm(const float* x, float* y, const float* gamma, const float* beta, long rows, int C, float eps,

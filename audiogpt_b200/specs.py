@@ -533,6 +533,64 @@ def synth_vae_decoder(cfg, seed: int = 5150):
     return synth_state_dict(vae_decoder_param_shapes(cfg), seed, convtranspose_prefixes=())
 
 
+# ---------------------------------------------------------------------------------------------- PitchExtractor
+PE_BASE = dict(n_mel_bins=80, hidden_size=256, conv_layers=2, predictor_hidden=256, predictor_layers=5, predictor_kernel=5)
+PE_SMALL = dict(n_mel_bins=80, hidden_size=32, conv_layers=2, predictor_hidden=32, predictor_layers=5, predictor_kernel=5)
+
+
+def pe_param_shapes(cfg) -> "OrderedDict[str, Tuple[int, ...]]":
+    """State-dict layout (incl. the BatchNorm buffers) of NeuralSeq/modules/fastspeech/pe.py:119-134 PitchExtractor:
+    mel_prenet (Prenet :7-42), mel_encoder (ConvStacks :82-116) and pitch_predictor (tts_modules.py:217-245)."""
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    H, M, P = int(cfg["hidden_size"]), int(cfg["n_mel_bins"]), int(cfg["predictor_hidden"])
+    k = int(cfg["predictor_kernel"])
+    cin = M
+    for l in range(3):
+        s[f"mel_prenet.layers.{l}.0.weight"] = (H, cin, 5); s[f"mel_prenet.layers.{l}.0.bias"] = (H,)
+        s[f"mel_prenet.layers.{l}.2.weight"] = (H,); s[f"mel_prenet.layers.{l}.2.bias"] = (H,)
+        s[f"mel_prenet.layers.{l}.2.running_mean"] = (H,); s[f"mel_prenet.layers.{l}.2.running_var"] = (H,)
+        s[f"mel_prenet.layers.{l}.2.num_batches_tracked"] = ()
+        cin = H
+    s["mel_prenet.out_proj.weight"] = (H, H); s["mel_prenet.out_proj.bias"] = (H,)
+    for l in range(int(cfg["conv_layers"])):
+        s[f"mel_encoder.conv.{l}.conv.conv.weight"] = (H, H, 5); s[f"mel_encoder.conv.{l}.conv.conv.bias"] = (H,)
+        s[f"mel_encoder.conv.{l}.norm.weight"] = (H,); s[f"mel_encoder.conv.{l}.norm.bias"] = (H,)
+    if int(cfg["conv_layers"]) > 0:
+        s["mel_encoder.in_proj.weight"] = (H, H); s["mel_encoder.in_proj.bias"] = (H,)
+        s["mel_encoder.out_proj.weight"] = (H, H); s["mel_encoder.out_proj.bias"] = (H,)
+    s["pitch_predictor.pos_embed_alpha"] = (1,)
+    cin = H
+    for l in range(int(cfg["predictor_layers"])):
+        s[f"pitch_predictor.conv.{l}.1.weight"] = (P, cin, k); s[f"pitch_predictor.conv.{l}.1.bias"] = (P,)
+        s[f"pitch_predictor.conv.{l}.3.weight"] = (P,); s[f"pitch_predictor.conv.{l}.3.bias"] = (P,)
+        cin = P
+    s["pitch_predictor.linear.weight"] = (2, P); s["pitch_predictor.linear.bias"] = (2,)
+    s["pitch_predictor.embed_positions._float_tensor"] = (1,)
+    return s
+
+
+def synth_pe(cfg, seed: int = 606):
+    """Seeded PitchExtractor weights; BatchNorm running statistics are made valid (var > 0)."""
+    shapes = pe_param_shapes(cfg)
+    sd = synth_state_dict({k: v for k, v in shapes.items() if len(v) > 0}, seed)
+    out: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for i, (k, shp) in enumerate(shapes.items()):
+        if k.endswith("num_batches_tracked"):
+            out[k] = torch.tensor(0, dtype=torch.long)
+        elif k.endswith("running_var"):
+            g = torch.Generator().manual_seed(seed * 7919 + i)
+            out[k] = 0.5 + torch.rand(shp, generator=g)
+        elif k.endswith("running_mean"):
+            out[k] = sd[k] * 4.0                  # N(0, 0.2^2)
+        elif k.endswith("pos_embed_alpha"):
+            out[k] = torch.tensor([0.7])
+        elif k.endswith("_float_tensor"):
+            out[k] = torch.zeros(1)
+        else:
+            out[k] = sd[k]
+    return out
+
+
 def synth_diffnet(cfg, seed: int = 2024):
     return synth_state_dict(diffnet_param_shapes(cfg), seed)
 

@@ -234,6 +234,27 @@ int agpt_vae_create(const agpt_vae_cfg* cfg, const float* const* host_weights, i
 /* z [B, embed_dim, H, W] (device) -> out [B, out_ch, H * 2^(levels-1), W * 2^(levels-1)] (device) */
 int agpt_vae_decode(agpt_handle h, const float* z, int B, int H, int W, float* out, void* stream);
 
+/* ------------------------------------------------------------------ PitchExtractor
+ * Replaces PitchExtractor.forward (NeuralSeq/modules/fastspeech/pe.py:119-148: Prenet :7-42, ConvStacks :82-116,
+ * PitchPredictor modules/fastspeech/tts_modules.py:217-260, denorm_f0 utils/pitch_utils.py:63-76): F0 from a generated
+ * mel for the NSF vocoder (inference/svs/base_svs_infer.py run_vocoder).                                          */
+typedef struct {
+  int n_mel_bins;          /* 80 */
+  int hidden_size;         /* hparams['hidden_size'] */
+  int conv_layers;         /* ConvStacks layers (2) */
+  int predictor_hidden;    /* hparams['predictor_hidden'] or hidden_size */
+  int predictor_layers;    /* 5 */
+  int predictor_kernel;    /* hparams['predictor_kernel'] */
+} agpt_pe_cfg;
+/* host_weights: fp32 HOST arrays in the key order of audiogpt_b200.specs.pe_param_shapes(cfg) (state-dict order incl. the
+ * BatchNorm buffers; num_batches_tracked and embed_positions._float_tensor are passed and ignored).               */
+int agpt_pe_create(const agpt_pe_cfg* cfg, const float* const* host_weights, int n_weights, int device, agpt_handle* out);
+/* mel [B][T][n_mel_bins] (device, channels-last as the reference passes it) -> pitch_pred [B][T][2], f0_denorm [B][T].
+ * pitch_norm: 0 none, 1 'standard' (f0 * std + mean), 2 'log' (2 ** f0); use_uv: zero F0 where pitch_pred[..., 1] > 0;
+ * all-zero mel frames (padding) give F0 = 0.                                                                      */
+int agpt_pe_forward(agpt_handle h, const float* mel, int B, int T, float* pitch_pred, float* f0_denorm, int use_uv,
+                    int pitch_norm, float f0_mean, float f0_std, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -285,6 +285,25 @@ def golden_diffusion():
     save("diffusion_base_fwd", eps=eb)
 
 
+def golden_pe():
+    """PitchExtractor (NeuralSeq/modules/fastspeech/pe.py:119-148), small and base widths, ragged + padded mels."""
+    from utils.hparams import hparams
+    from modules.fastspeech.pe import PitchExtractor
+    for name, cfg, B, T in (("pe_small", specs.PE_SMALL, 2, 37), ("pe_base", specs.PE_BASE, 2, 150)):
+        hparams.clear()
+        hparams.update(hidden_size=cfg["hidden_size"], predictor_hidden=cfg["predictor_hidden"], ffn_padding="SAME",
+                       predictor_kernel=cfg["predictor_kernel"], pitch_type="frame", use_uv=True, pitch_norm="log", dropout=0.1)
+        pe = PitchExtractor(cfg["n_mel_bins"], conv_layers=cfg["conv_layers"])
+        print("pe load:", pe.load_state_dict(specs.synth_pe(cfg, 606), strict=True))
+        pe.eval()
+        mel = specs.synth_tensor((B, T, 80), seed=71, scale=1.0, shift=-2.5)
+        mel[1, -T // 5:] = 0                      # padded tail (all-zero frames)
+        with torch.no_grad():
+            r = pe(mel)
+        print(name, "pitch_pred rms", r["pitch_pred"].pow(2).mean().sqrt().item(), "f0 max", r["f0_denorm_pred"].max().item())
+        save(name, pitch_pred=r["pitch_pred"], f0_denorm_pred=r["f0_denorm_pred"])
+
+
 def golden_c3_full():
     """BASELINE configs[2] at full size: DiffNet base (20 x 256), B=16, T=400, 100 ancestral p_sample steps
     with the per-step noise of SURVEY.md 8d (seed 4), run by the reference's own GaussianDiffusion."""
@@ -493,10 +512,10 @@ def golden_vae():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["hifigan", "diffusion", "c3", "ldm", "bigvgan", "vae"]   # extra selector: ldm100 (DDIM-100 end point only)
+    which = sys.argv[1:] or ["hifigan", "diffusion", "c3", "pe", "ldm", "bigvgan", "vae"]   # extra selector: ldm100 (DDIM-100 end point only)
     if "nsf" in which:
         which = list(which) + ["hifigan_nsf_only"]
-    if "hifigan" in which or "diffusion" in which or "c3" in which or "hifigan_nsf_only" in which:
+    if "hifigan" in which or "diffusion" in which or "c3" in which or "pe" in which or "hifigan_nsf_only" in which:
         import_neuralseq()
         cwd = os.getcwd()
         os.chdir(os.path.join(REF, "NeuralSeq"))
@@ -507,6 +526,8 @@ if __name__ == "__main__":
                 golden_diffusion()
             if "c3" in which:
                 golden_c3_full()
+            if "pe" in which:
+                golden_pe()
         finally:
             os.chdir(cwd)
     if "ldm" in which or "ldm100" in which:

@@ -69,7 +69,7 @@ def test_install_aliases_reference_module_names():
             "print(len(p))") % ROOT
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stderr
-    assert r.stdout.strip() == "7"
+    assert r.stdout.strip() == "8"
 
 
 def test_install_keeps_reference_unet_for_unsupported_configs(tmp_path):

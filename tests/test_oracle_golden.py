@@ -222,6 +222,20 @@ def test_c3_full_chain():
     assert rel_rmse(dr.denorm_spec(x[:, 0].transpose(1, 2), smin, smax)[:, ::4, :], g["mel_end"]) < 1e-4
 
 
+def test_pitch_extractor_oracle_vs_reference():
+    """oracle/pe_ref.py == the reference's PitchExtractor (fixtures: make_golden.py pe), padded tail included."""
+    from oracle import pe_ref
+    for name, cfg, B, Tn in (("pe_small", specs.PE_SMALL, 2, 37), ("pe_base", specs.PE_BASE, 2, 150)):
+        g = load_golden(name)
+        mel = specs.synth_tensor((B, Tn, 80), seed=71, scale=1.0, shift=-2.5)
+        mel[1, -Tn // 5:] = 0
+        r = pe_ref.pe_forward(specs.synth_pe(cfg, 606), cfg, mel)
+        assert rmse(r["pitch_pred"], g["pitch_pred"]) < 1e-6 and rmse(r["f0_denorm_pred"], g["f0_denorm_pred"]) < 1e-6
+    n = sum(int(np.prod(v)) for k, v in specs.pe_param_shapes(specs.PE_BASE).items()
+            if not k.endswith(("running_mean", "running_var", "num_batches_tracked", "_float_tensor")))
+    assert n == 3_257_091                                  # parameters of the reference module at hidden 256
+
+
 def test_bigvgan_small():
     """oracle/bigvgan_ref.py == the reference's BigVGAN module (fixture made by make_golden.py bigvgan)."""
     from oracle import bigvgan_ref as br
