@@ -306,17 +306,24 @@ class LatentDiffusionShim(torch.nn.Module):
     benchmark and tests; inside AudioGPT the real LatentDiffusion object plays this role."""
 
     class _Wrapper(torch.nn.Module):
-        def __init__(self, unet):
+        """DiffusionWrapper.forward (ddpm.py:1400-1409) for the conditioning keys a cross-attention UNet can take:
+        'crossattn' (text-to-audio) and 'hybrid' (channel-concatenated conditioning + cross-attention)."""
+
+        def __init__(self, unet, conditioning_key="crossattn"):
             super().__init__()
+            assert conditioning_key in ("crossattn", "hybrid")
             self.diffusion_model = unet
-            self.conditioning_key = "crossattn"
+            self.conditioning_key = conditioning_key
 
-        def forward(self, x, t, c_crossattn=None):
-            return self.diffusion_model(x, t, context=torch.cat(c_crossattn, 1))
+        def forward(self, x, t, c_concat=None, c_crossattn=None):
+            cc = torch.cat(c_crossattn, 1)
+            if self.conditioning_key == "hybrid":
+                x = torch.cat([x] + c_concat, dim=1)
+            return self.diffusion_model(x, t, context=cc)
 
-    def __init__(self, unet, timesteps=1000, linear_start=0.00085, linear_end=0.012):
+    def __init__(self, unet, timesteps=1000, linear_start=0.00085, linear_end=0.012, conditioning_key="crossattn"):
         super().__init__()
-        self.model = self._Wrapper(unet)
+        self.model = self._Wrapper(unet, conditioning_key)
         betas = (torch.linspace(linear_start ** 0.5, linear_end ** 0.5, timesteps, dtype=torch.float64) ** 2).numpy()
         ac = np.cumprod(1. - betas, axis=0)
         f32 = lambda a: torch.tensor(a, dtype=torch.float32)

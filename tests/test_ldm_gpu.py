@@ -121,6 +121,34 @@ def test_ddim100_full_chain_vs_reference():
     assert rel_rmse(inter2["pred_x0"][-1].cpu(), g["pred_x0_last"]) < 2e-3
 
 
+def test_hybrid_conditioning_stepwise_path_vs_oracle():
+    """DiffusionWrapper 'hybrid' mode (ddpm.py:1404-1408: channel-concatenated conditioning + cross-attention) with
+    dict conditionings through DDIMSampler: not the fused crossattn case, so the sampler takes the step-wise path
+    (apply_model -> UNet forward -> agpt_ddim_update per step), with classifier-free guidance on dict conditionings
+    (ddim.py:183-195).  Compared with the oracle sampler driving the oracle UNet the same way."""
+    from oracle import ldm_ref as lr
+    cfg = dict(specs.UNET_SMALL, in_channels=8)            # 4 latent + 4 concatenated conditioning channels
+    u = build(cfg, 3131)
+    sd = specs.synth_unet(cfg, 3131)
+    ldm = LatentDiffusionShim(u, conditioning_key="hybrid").to("cuda")
+    smp = DDIMSampler(ldm)
+    N, H, W, S = 2, 6, 10, 7
+    xT = specs.synth_tensor((N, 4, H, W), seed=1)
+    cc = specs.synth_tensor((N, 4, H, W), seed=2)          # e.g. a masked-mel latent
+    ctx = specs.synth_tensor((N, S, cfg["context_dim"]), seed=3)
+    uctx = specs.synth_tensor((1, S, cfg["context_dim"]), seed=4).expand(N, -1, -1).contiguous()
+    cond = {"c_concat": [cc.cuda()], "c_crossattn": [ctx.cuda()]}
+    ucond = {"c_concat": [cc.cuda()], "c_crossattn": [uctx.cuda()]}
+    out, inter = smp.sample(S=10, batch_size=N, shape=(4, H, W), conditioning=cond, verbose=False, x_T=xT.cuda(), eta=0.0,
+                            unconditional_guidance_scale=1.5, unconditional_conditioning=ucond)
+    assert len(inter["x_inter"]) >= 2                       # the step-wise path logs like the reference
+    eps_fn = lambda x, t, c: lr.unet_forward(sd, cfg, torch.cat([x, torch.cat([cc] * (x.shape[0] // N))], 1), t, c)
+    ref = lr.ddim_sample(eps_fn, lr.ldm_schedule()["alphas_cumprod"], 10, xT, ctx, uctx, 1.5)
+    e = rel_rmse(out.cpu(), ref)
+    print("hybrid conditioning DDIM-10 + CFG rel-RMSE vs oracle:", e)
+    assert e < 1e-3
+
+
 def test_context_cache_survives_freed_source():
     """the hoisted K/V cache is keyed on the caller's tensor; a half-precision context is converted,
     so the source could be freed and its address reused by another prompt of the same shape."""
