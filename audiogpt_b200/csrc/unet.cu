@@ -58,7 +58,6 @@ struct Unet : Handle {
   DevBuf ctx_kv;
   DevBuf arena;
   size_t arena_off = 0, arena_cap = 0;
-  DevBuf gn_scratch_f;  // doubles stored in a float buffer (2 floats per double)
   DevBuf ddim_eps, ddim_x, ddim_p0;
   // denoising-loop state: per-step tables on the device, a device step counter, one captured step (CUDA graph)
   DevBuf emb_table, emb_cur, coef_table, tsteps_dev, step_ctr;
@@ -114,13 +113,12 @@ struct Unet : Handle {
 
   float* run_res(const ResW& r, const float* x, const float* emb_out, int N, int H, int W, cudaStream_t s) {
     const int HW = H * W;
-    double* scr = reinterpret_cast<double*>(gn_scratch_f.p);
     float* h1 = alloc((size_t)N * HW * r.cin);
-    groupnorm(x, h1, r.gn1_g.p, r.gn1_b.p, N, HW, r.cin, 32, 1e-5f, true, scr, s);
+    groupnorm(x, h1, r.gn1_g.p, r.gn1_b.p, N, HW, r.cin, 32, 1e-5f, true, nullptr, s);
     float* h2 = alloc((size_t)N * HW * r.cout);
     conv3x3(r.conv1, h1, h2, N, H, W, EPI_ADDVEC, nullptr, emb_out + r.emb_off, emb_gstride, s);
     float* h3 = alloc((size_t)N * HW * r.cout);
-    groupnorm(h2, h3, r.gn2_g.p, r.gn2_b.p, N, HW, r.cout, 32, 1e-5f, true, scr, s);
+    groupnorm(h2, h3, r.gn2_g.p, r.gn2_b.p, N, HW, r.cout, 32, 1e-5f, true, nullptr, s);
     const float* sk = x;
     if (r.has_skip) {
       float* skb = alloc((size_t)N * HW * r.cout);
@@ -236,9 +234,8 @@ struct Unet : Handle {
     const int HW = H * W;
     const long rows = (long)N * HW;
     const int C = t.inner;
-    double* scr = reinterpret_cast<double*>(gn_scratch_f.p);
     float* xn = alloc(rows * t.ch);
-    groupnorm(x, xn, t.gn_g.p, t.gn_b.p, N, HW, t.ch, 32, 1e-6f, false, scr, s);
+    groupnorm(x, xn, t.gn_g.p, t.gn_b.p, N, HW, t.ch, 32, 1e-6f, false, nullptr, s);
     float* h = alloc(rows * C);
     linear(t.proj_in, xn, t.ch, h, C, rows, EPI_BIAS, nullptr, 0, s);
     float* a = alloc(rows * C);
@@ -340,7 +337,6 @@ struct Unet : Handle {
     AGPT_CHECK(N >= 1 && N <= 256 && H >= 1 && W >= 1, "bad UNet input shape");
     const size_t need = arena_need(N, H, W);
     if (need > arena_cap) { arena.ensure(need); arena_cap = need; }
-    gn_scratch_f.ensure(64);
   }
 
   // everything after the embedding: x [Nsrc][C][H][W] (sample n reads n % Nsrc) -> eps [N][Cout][H][W]
@@ -361,7 +357,7 @@ struct Unet : Handle {
       a = run_block(b, Act{cat, a.C + sk.C, a.H, a.W}, emb_out, N, s);
     }
     float* hn = alloc((size_t)N * a.H * a.W * a.C);
-    groupnorm(a.p, hn, out_gn_g.p, out_gn_b.p, N, a.H * a.W, a.C, 32, 1e-5f, true, reinterpret_cast<double*>(gn_scratch_f.p), s);
+    groupnorm(a.p, hn, out_gn_g.p, out_gn_b.p, N, a.H * a.W, a.C, 32, 1e-5f, true, nullptr, s);
     if (!eps) {
       conv_out_ddim(hn, out_w9c4.p, out_b4.p, ddim_x.p, ddim_p0.p, coef_table.p, reinterpret_cast<const int*>(step_ctr.p),
                     Nsrc, a.H, a.W, a.C, N == Nsrc ? 1 : 0, s);

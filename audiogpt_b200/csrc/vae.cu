@@ -46,7 +46,6 @@ struct Vae : Handle {
   std::vector<VLevel> levels;
   DevBuf gno, bno;
   DevBuf buf[6], qkv, sc, kT, vpad, zcl;
-  DevBuf gn_dummy;
 
   // strips of at most 78 columns: virtual width 80, halo tile of 128 + 2*80 + 2 rows -- the largest operand tile
   // the one-tile-per-CTA kernel fits next to its staging buffer (the UNet's 78-column maps use the same budget)
