@@ -134,6 +134,54 @@ def all_gather_rows(x: torch.Tensor, counts: Sequence[int] = None) -> torch.Tens
     return torch.cat([out[r * m: r * m + counts[r]] for r in range(world)], dim=0)
 
 
+class P2PGather:
+    """All-gather of finished per-rank row blocks over NVLink by the COPY ENGINES, not by SM kernels: every rank owns
+    a gather buffer [world, *block]; the buffers are exchanged once as CUDA IPC handles (the mechanism
+    ``torch.multiprocessing`` uses to share CUDA tensors), and ``submit(x)`` issues one peer ``cudaMemcpyAsync`` per
+    destination (``tensor.copy_`` between devices) on a side stream that waits on the producing stream through an
+    event.  Nothing of it runs on the SMs, so a persistent 148-CTA compute grid is not disturbed (an NCCL all-gather
+    kernel launched under such a grid delays whichever CTAs it displaces: round 1 lost 3.7 points of weak-scaling
+    efficiency there).  ``drain()`` waits for this rank's copies and meets the other ranks at a barrier; after it,
+    ``gathered(slot)`` holds every rank's block.  Double-buffered: consecutive submits alternate between two slots."""
+
+    def __init__(self, block_shape, dtype=torch.float32, device=None, slots: int = 2):
+        from torch.multiprocessing.reductions import reduce_tensor
+        assert dist.is_initialized() and dist.get_world_size() > 1
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.slots = slots
+        self.buf = torch.zeros((slots, self.world) + tuple(block_shape), dtype=dtype, device=self.dev)
+        fn, args = reduce_tensor(self.buf)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, args)
+        self.peers = []
+        for r in range(self.world):
+            self.peers.append(self.buf if r == self.rank else fn(*handles[r]))
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.n = 0
+        dist.barrier()
+
+    def submit(self, x: torch.Tensor):
+        slot = self.n % self.slots
+        self.n += 1
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        x.record_stream(self.stream)                    # the block must outlive the asynchronous copies
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            for r in range(self.world):
+                self.peers[r][slot, self.rank].copy_(x, non_blocking=True)
+        return slot
+
+    def drain(self):
+        torch.cuda.current_stream(self.dev).wait_stream(self.stream)
+        self.stream.synchronize()
+        dist.barrier()
+
+    def gathered(self, slot: int) -> torch.Tensor:
+        return self.buf[slot].reshape((-1,) + tuple(self.buf.shape[3:]))
+
+
 # ---- mixed dispatch (BASELINE configs[4]): greedy longest-processing-time assignment ----
 HIFIGAN_GFLOP_PER_FRAME = 0.614          # V1, SURVEY.md 8d
 DDIM100_TFLOP_PER_CLIP = 18.66 + 0.39    # UNet x200 forwards + VAE decode

@@ -419,7 +419,14 @@ def run_ours(args):
     mel_host = specs.synth_tensor((B_PER_GPU, 80, T_FRAMES), seed=100 + rank, scale=2.0, shift=-4.0)
     mel = mel_host.to(dev)
     frames_step = B_PER_GPU * T_FRAMES * n_gpus
-    gather = parallel.AsyncGather() if n_gpus > 1 else None
+    # finished waveforms -> every rank: copy engines over NVLink (parallel.P2PGather, no SM kernel under the persistent
+    # compute grid); AGPT_GATHER=nccl selects the asynchronous NCCL all-gather instead
+    gather, gather_kind = None, None
+    if n_gpus > 1:
+        if os.environ.get("AGPT_GATHER", "p2p") == "p2p":
+            gather, gather_kind = parallel.P2PGather((B_PER_GPU, 1, T_FRAMES * HOP), device=dev), "p2p_copy_engine"
+        else:
+            gather, gather_kind = parallel.AsyncGather(), "nccl_async"
 
     def barrier():
         if n_gpus > 1:
@@ -582,7 +589,8 @@ def run_ours(args):
             "x_realtime": value * HOP / SR, "x_realtime_per_gpu": value * HOP / SR / n_gpus,
             "tflops_fp32": 0.614e9 * value / 1e12,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "ddim": ddim, "mixed_dispatch": mixed, "extra": extra}
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "ddim": ddim, "mixed_dispatch": mixed, "extra": extra,
+            "waveform_gather": gather_kind}
     print(json.dumps(line))
     sys.stdout.flush()
     finish()
