@@ -55,7 +55,7 @@ struct TapConvParams {
   int epi; const float* res; long res_gstride; int res_pitch; float scale; int accumulate;
   const float* evec; int evec_gstride;
   float* out2; long out2_gstride; int out2_pitch; int csplit;
-  const float* w_h; const float* w_h256; const float* w_h64; int tc_chunks_h; float tc_descale;   // fp16 hi/lo image (tcconv5.cu): 64-channel chunks, weights pre-scaled by 1/tc_descale
+  const float* w_h; const float* w_h256; const float* w_h64; const float* w_h96; int tc_chunks_h; float tc_descale;   // fp16 hi/lo image (tcconv5.cu): 64-channel chunks, weights pre-scaled by 1/tc_descale
   int tc_bn, tc_na, tc_nw, tc_nr, tc_nwk, tc_nb, tc_tps, tc_flags, tc_flags_user;   // tc_bn == 0 => FMA only
   long long* dbg;      // optional per-CTA phase timestamps (tc_flags & 2)
   float flops_scale;   // useful fraction of the MACs (zero-padded polyphase taps); 0 => 1
@@ -109,7 +109,7 @@ void make_planes(const float* x, __half* hi, __half* lo, long n, int pro, float 
 
 // ---------------------------------------------------------------- host side
 struct PackedConv {
-  DevBuf w, b, w_h, w_h256, w_h64;
+  DevBuf w, b, w_h, w_h256, w_h64, w_h96;
   int tc_bn = 0, h_chunks = 0;
   float h_descale = 1.f;
   int Cin = 0, cin_pad = 0, Cout = 0, cout_pad = 0, ntaps = 0;
@@ -133,7 +133,7 @@ void tcconv_launch(TapConvParams P, cudaStream_t st);          // tcgen05 dispat
 bool tcconv5_launch(TapConvParams P, cudaStream_t st);
 bool tcconv6_launch(TapConvParams P, cudaStream_t st, bool force);
 struct HTile { int bn; const float* w; long ntiles; };
-HTile pick_h_tile(const TapConvParams& P, int sms);   // tile width for the fp16 kernels (tcconv5.cu)
+HTile pick_h_tile(const TapConvParams& P, int sms, bool with96 = true);   // tile width for the fp16 kernels (tcconv5.cu); 96 exists in tcconv5 only
 void pack_h_weights(struct PackedConv& pc, const std::vector<float>& h);
 bool tcconv_supported(const TapConvParams& P);
 void pack_tc_weights(struct PackedConv& pc, const std::vector<float>& h);
@@ -168,7 +168,7 @@ inline TapConvParams tapconv_params(const PackedConv& pc, int G, int L, int Wrea
   P.scale = 1.f;
   P.flops_scale = pc.useful;
   P.tc_bn = pc.tc_bn;
-  P.w_h = pc.w_h.p; P.w_h256 = pc.w_h256.p; P.w_h64 = pc.w_h64.p; P.tc_chunks_h = pc.h_chunks; P.tc_descale = pc.h_descale;
+  P.w_h = pc.w_h.p; P.w_h256 = pc.w_h256.p; P.w_h64 = pc.w_h64.p; P.w_h96 = pc.w_h96.p; P.tc_chunks_h = pc.h_chunks; P.tc_descale = pc.h_descale;
   return P;
 }
 

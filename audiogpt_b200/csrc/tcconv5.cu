@@ -49,6 +49,9 @@ __host__ __device__ inline void tc5_layout(Tc5Smem& s, int BN, int RRA, int NA, 
 
 constexpr int V5_THREADS = 320;   // 8 worker warps (0-3, 6-9) + warp 4 (MMA issuer) + warp 5 (weight producer)
 
+// TMEM allocations are powers of two >= 32 columns
+__host__ __device__ constexpr int tmem_cols(int bn) { return bn <= 32 ? 32 : (bn <= 64 ? 64 : (bn <= 128 ? 128 : 256)); }
+
 template <int BN, int NWK>
 __global__ void __launch_bounds__(NWK == 256 ? V5_THREADS : 192, 1) tcconv5_kernel(const __grid_constant__ TapConvParams P) {
   extern __shared__ uint8_t smem_raw_[];
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(NWK == 256 ? V5_THREADS : 192, 1) tcconv5_kern
   }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)(BN < 32 ? 32 : BN)) : "memory");
+                 ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)tmem_cols(BN)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (is_worker) {
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(NWK == 256 ? V5_THREADS : 192, 1) tcconv5_kern
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(BN < 32 ? 32 : BN)) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols(BN)) : "memory");
   }
 }
 
@@ -361,6 +364,7 @@ void pack_h_weights(PackedConv& pc, const std::vector<float>& h) {
   build_h_image(pc, h, pc.tc_bn, wscale, pc.w_h);
   if (pc.Cout % 256 == 0) build_h_image(pc, h, 256, wscale, pc.w_h256);
   if (pc.tc_bn == 128) build_h_image(pc, h, 64, wscale, pc.w_h64);   // narrower tiles for launches that would not fill the SMs
+  if (pc.tc_bn == 128 && pc.Cout > 128) build_h_image(pc, h, 96, wscale, pc.w_h96);
 }
 
 // Try one tile width; returns false when it does not fit the shared-memory budget.
@@ -403,6 +407,7 @@ static bool tcconv5_try(TapConvParams P, int BN, cudaStream_t st) {
   if (!attr_done_dev[dev & 63]) {
     AGPT_CUDA(cudaFuncSetAttribute(tcconv5_kernel<256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
     AGPT_CUDA(cudaFuncSetAttribute(tcconv5_kernel<128, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
+    AGPT_CUDA(cudaFuncSetAttribute(tcconv5_kernel<96, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
     AGPT_CUDA(cudaFuncSetAttribute(tcconv5_kernel<64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
     AGPT_CUDA(cudaFuncSetAttribute(tcconv5_kernel<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
     AGPT_CUDA(cudaFuncSetAttribute(tcconv5_kernel<32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
@@ -410,21 +415,24 @@ static bool tcconv5_try(TapConvParams P, int BN, cudaStream_t st) {
   }
   if (BN == 256) tcconv5_kernel<256, 256><<<grid, nthreads, smem, st>>>(P);
   else if (BN == 128) tcconv5_kernel<128, 256><<<grid, nthreads, smem, st>>>(P);
+  else if (BN == 96) tcconv5_kernel<96, 256><<<grid, nthreads, smem, st>>>(P);
   else if (BN == 64) tcconv5_kernel<64, 256><<<grid, nthreads, smem, st>>>(P);
   else if (P.tc_nwk == 128) tcconv5_kernel<32, 128><<<grid, nthreads, smem, st>>>(P);
   else tcconv5_kernel<32, 256><<<grid, nthreads, smem, st>>>(P);
   return true;
 }
 
-// Tile width: the candidate (256 / native 128|64|32 / 64 for native-128 layers) with the smallest
+// Tile width: the candidate (256 / native 128|64|32 / 96 and 64 for native-128 layers) with the smallest
 // waves x per-tile cost, where waves = ceil(tiles / SMs).  Per-tile cost relative to BN = 128 from the
 // micro-benchmarks (profiles/r1e_*): wider tiles amortise the activation operand, narrower ones fill the SMs.
-HTile pick_h_tile(const TapConvParams& P, int sms) {
+HTile pick_h_tile(const TapConvParams& P, int sms, bool with96) {
   static int allow256 = -1;
   if (allow256 < 0) { const char* e = getenv("AGPT_TC_BN256"); allow256 = (e && e[0] == '0') ? 0 : 1; }
   const int Lv = tc_lv(P);
   const long rt = (long)cdiv(Lv, TC_ROWS) * tc_groups(P);
-  auto cost = [](int bn) { return bn == 256 ? 1.7 : (bn == 128 ? 1.0 : (bn == 64 ? 0.62 : 0.45)); };
+  static int allow96 = -1;
+  if (allow96 < 0) { const char* e = getenv("AGPT_TC_BN96"); allow96 = (e && e[0] == '0') ? 0 : 1; }
+  auto cost = [](int bn) { return bn == 256 ? 1.7 : (bn == 128 ? 1.0 : (bn == 96 ? 0.82 : (bn == 64 ? 0.62 : 0.45))); };
   HTile best{P.tc_bn, P.w_h, rt * cdiv(P.Cout, P.tc_bn)};
   double bs = (double)cdiv(best.ntiles, (long)sms) * cost(P.tc_bn);
   auto consider = [&](int bn, const float* w) {
@@ -435,6 +443,7 @@ HTile pick_h_tile(const TapConvParams& P, int sms) {
   };
   if (allow256) consider(256, P.w_h256);
   if (P.tc_bn == 128) consider(64, P.w_h64);
+  if (P.tc_bn == 128 && allow96 && with96) consider(96, P.w_h96);   // e.g. 640 channels on 16 row tiles: 112 tiles in one wave
   return best;
 }
 

@@ -686,7 +686,7 @@ bool tcconv6_launch(TapConvParams P, cudaStream_t st, bool force) {
   static int sms_dev[64] = {0};
   if (!sms_dev[dev & 63]) AGPT_CUDA(cudaDeviceGetAttribute(&sms_dev[dev & 63], cudaDevAttrMultiProcessorCount, dev));
   const int sms = sms_dev[dev & 63];
-  const HTile c = pick_h_tile(P, sms);
+  const HTile c = pick_h_tile(P, sms, false);
   if (!force && c.ntiles <= sms) return false;
   if (c.bn != P.tc_bn) {
     TapConvParams Q = P;

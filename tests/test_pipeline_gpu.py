@@ -77,6 +77,7 @@ SHAPES = [  # G, L, Cin, Cout, K, dil, Wreal
     (3, 400, 256, 512, 3, 2, 0), (1, 777, 320, 320, 1, 1, 0), (2, 780, 320, 320, 3, 1, 78),
     (2, 195, 640, 640, 3, 1, 39), (1, 130, 1280, 320, 1, 1, 0), (2, 4, 64, 96, 3, 1, 0),
     (2, 300, 80, 256, 7, 1, 0), (1, 780, 4, 320, 3, 1, 78), (2, 500, 96, 40, 5, 2, 0),
+    (8, 195, 640, 640, 3, 1, 39),   # 16 row tiles x 640 channels: the 96-wide tile (112 tiles, last column tile partial)
 ]
 
 
