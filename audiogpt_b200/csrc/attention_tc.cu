@@ -362,6 +362,343 @@ void launch_at(const float* q, int q_pitch, const float* k, int k_pitch, const f
   attention_tc_kernel<D><<<grid, 128, smem, st>>>(q, q_pitch, k, k_pitch, v, v_pitch, o, o_pitch, Lq, Lk, qscale, phi, plo);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Plane-fed variant: q, k, v arrive as fp16 hi/lo operand planes (written by the epilogue of the projection GEMMs),
+// so the K / V blocks go from global memory straight into the swizzled operand tiles with cp.async -- no fp32 -> fp16
+// conversions in the key loop (the ncu source view of the fp32-input kernel above charges half of its stall samples
+// to F2FP, the quarter-rate conversion pipe: profiles/r2k_attention_findings.md).  What is left on that pipe is
+// exp2 and the split of P.
+//   * 8 warps: warp w and w + 4 share a TMEM lane quadrant and split the 64 keys of a block (32 columns of S each),
+//     each with its own running max / sum / accumulator (O_blk goes to two TMEM accumulators, one per key half);
+//     the two partial softmaxes merge once, after the last block.  Twice the warps per SM hide the conversion latency.
+//   * V is consumed as it lies in memory, [keys][d]: an MN-major B operand (instruction-descriptor bit 16), the tile
+//     layout is the K tile's.  VT = true keeps the transposed K-major tile of the kernel above as the A/B variant.
+//   * single K and V buffers: K(i+1) is fetched while block i's softmax runs, V(i+1) while block i+1's S runs.
+template <int D>
+struct ApCfg {
+  static constexpr int NCH = (D + 63) / 64;
+  static constexpr int DP = (D + 15) / 16 * 16;
+  static constexpr int C8 = D / 8;                                        // 16-byte chunks per row
+  static constexpr uint32_t Q_BYTES = 2u * NCH * AT_ROWS * 128;
+  static constexpr uint32_t K_BYTES = 2u * NCH * AT_BK * 128;
+  static constexpr uint32_t V_BYTES = K_BYTES;                            // the transposed variant needs 2 * DP * 128 <= this
+  static constexpr uint32_t P_BYTES = 2u * AT_ROWS * 128;
+  static constexpr uint32_t TOTAL = Q_BYTES + K_BYTES + V_BYTES + P_BYTES;
+  static constexpr uint32_t TMEM_COLS = (AT_BK + 2 * DP <= 128) ? 128 : 256;
+  static constexpr int MINB = (D <= 64) ? 2 : 1;
+};
+
+__device__ __forceinline__ void at_cp16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+template <int N_>
+__device__ __forceinline__ void at_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+// MN-major SWIZZLE_128B descriptor: LBO = stride between 64-element blocks of the MN dimension, SBO = 1024 B (8 k-rows)
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int D, bool VT>
+__global__ void __launch_bounds__(256, ApCfg<D>::MINB) attention_pl_kernel(
+    const __half* __restrict__ qh, const __half* __restrict__ ql, int q_pitch,
+    const __half* __restrict__ kh, const __half* __restrict__ kl, int k_pitch,
+    const __half* __restrict__ vh, const __half* __restrict__ vl, int v_pitch,
+    float* __restrict__ o, int o_pitch, int Lq, int Lk, float qscale /* d^-0.5 * log2(e) */,
+    __half* __restrict__ phi, __half* __restrict__ plo) {
+  using Cf = ApCfg<D>;
+  extern __shared__ uint8_t at_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* q_hi = smem;
+  uint8_t* q_lo = q_hi + Cf::NCH * AT_ROWS * 128;
+  uint8_t* k_hi = smem + Cf::Q_BYTES;
+  uint8_t* k_lo = k_hi + Cf::NCH * AT_BK * 128;
+  uint8_t* v_hi = smem + Cf::Q_BYTES + Cf::K_BYTES;
+  uint8_t* v_lo = v_hi + (VT ? Cf::DP * 128 : Cf::NCH * AT_BK * 128);
+  uint8_t* p_hi = smem + Cf::Q_BYTES + Cf::K_BYTES + Cf::V_BYTES;
+  uint8_t* p_lo = p_hi + AT_ROWS * 128;
+  __shared__ uint64_t bar_s, bar_o;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, half = warp >> 2, row = quad * 32 + lane;
+  const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AT_ROWS;
+  if (tid == 0) { mbar_init(&bar_s, 1); mbar_init(&bar_o, 1); fence_barrier_init(); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_slot)), "r"(Cf::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // the tiles start as zeros: padding channels (d .. 64) are never written again, rows past Lk keep finite data
+  for (uint32_t i = tid; i < Cf::TOTAL / 16; i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+
+  const __half* kbh = kh + ((long)n * Lk) * k_pitch + h * D;
+  const __half* kbl = kl + ((long)n * Lk) * k_pitch + h * D;
+  const __half* vbh = vh + ((long)n * Lk) * v_pitch + h * D;
+  const __half* vbl = vl + ((long)n * Lk) * v_pitch + h * D;
+  auto issue_k = [&](int j0) {
+    for (int it = tid; it < AT_BK * Cf::C8; it += 256) {
+      const int r = it / Cf::C8, c8 = it - r * Cf::C8;
+      if (j0 + r >= Lk) continue;
+      const long src = (long)(j0 + r) * k_pitch + c8 * 8;
+      const uint32_t off = (uint32_t)(c8 >> 3) * (AT_BK * 128) + sw128(r, c8 & 7);
+      at_cp16(k_hi + off, kbh + src);
+      at_cp16(k_lo + off, kbl + src);
+    }
+  };
+  auto issue_v = [&](int j0) {
+    if (!VT) {
+      for (int it = tid; it < AT_BK * Cf::C8; it += 256) {
+        const int r = it / Cf::C8, c8 = it - r * Cf::C8;
+        if (j0 + r >= Lk) continue;
+        const long src = (long)(j0 + r) * v_pitch + c8 * 8;
+        const uint32_t off = (uint32_t)(c8 >> 3) * (AT_BK * 128) + sw128(r, c8 & 7);
+        at_cp16(v_hi + off, vbh + src);
+        at_cp16(v_lo + off, vbl + src);
+      }
+    } else {
+      // transposed tile [channel rows][64 keys]: lanes take consecutive keys
+      const int key = tid & 63, part = tid >> 6;
+      const bool kok = j0 + key < Lk;
+      for (int c8 = part; c8 < Cf::C8; c8 += 4) {
+        uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+        if (kok) {
+          a = *reinterpret_cast<const uint4*>(vbh + (long)(j0 + key) * v_pitch + c8 * 8);
+          b = *reinterpret_cast<const uint4*>(vbl + (long)(j0 + key) * v_pitch + c8 * 8);
+        }
+        const __half* ah = reinterpret_cast<const __half*>(&a);
+        const __half* bl = reinterpret_cast<const __half*>(&b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t off = sw128(c8 * 8 + i, key >> 3) + (uint32_t)(key & 7) * 2u;
+          *reinterpret_cast<__half*>(v_hi + off) = ah[i];
+          *reinterpret_cast<__half*>(v_lo + off) = bl[i];
+        }
+      }
+    }
+  };
+
+  // ---- Q tile (unscaled: the scale is applied to S), then the first K and V blocks
+  {
+    const __half* qbh = qh + ((long)n * Lq) * q_pitch + h * D;
+    const __half* qbl = ql + ((long)n * Lq) * q_pitch + h * D;
+    for (int it = tid; it < AT_ROWS * Cf::C8; it += 256) {
+      const int r = it / Cf::C8, c8 = it - r * Cf::C8;
+      if (q0 + r >= Lq) continue;
+      const long src = (long)(q0 + r) * q_pitch + c8 * 8;
+      const uint32_t off = (uint32_t)(c8 >> 3) * (AT_ROWS * 128) + sw128(r, c8 & 7);
+      at_cp16(q_hi + off, qbh + src);
+      at_cp16(q_lo + off, qbl + src);
+    }
+  }
+  issue_k(0);
+  cp_async_commit_();
+  issue_v(0);
+  cp_async_commit_();
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_base = ((uint32_t)(quad * 32)) << 16;
+  const uint32_t tm_s = tmem, tm_o = tmem + AT_BK;        // S: columns [0, 64); O_blk of key half x: [64 + x * DP, ...)
+  const uint32_t idesc_s = (1u << 4) | ((uint32_t)(AT_BK >> 3) << 17) | ((uint32_t)(AT_ROWS >> 4) << 24);
+  const uint32_t idesc_o = (1u << 4) | (VT ? 0u : (1u << 16)) | ((uint32_t)(Cf::DP >> 3) << 17) | ((uint32_t)(AT_ROWS >> 4) << 24);
+
+  float acc[Cf::DP];
+#pragma unroll
+  for (int c = 0; c < Cf::DP; ++c) acc[c] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+  const int nblk = (Lk + AT_BK - 1) / AT_BK;
+  uint32_t ph_s = 0, ph_o = 0;
+
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int j0 = blk * AT_BK;
+    at_cp_wait<1>();                 // everything but the youngest group (V of this block): Q and K(blk) have landed
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        uint32_t nz = 0;
+#pragma unroll
+        for (int c = 0; c < Cf::NCH; ++c) {
+          const int kv = (D - c * 64) < 64 ? (D - c * 64) : 64;
+          const int ksteps = (kv + 15) >> 4;
+          const uint64_t dqh = make_desc(smem_u32(q_hi + c * AT_ROWS * 128)), dql = make_desc(smem_u32(q_lo + c * AT_ROWS * 128));
+          const uint64_t dkh = make_desc(smem_u32(k_hi + c * AT_BK * 128)), dkl = make_desc(smem_u32(k_lo + c * AT_BK * 128));
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t ko = (uint64_t)(2 * ks);
+            at_umma_f16(tm_s, dqh + ko, dkh + ko, idesc_s, nz);
+            nz = 1u;
+            at_umma_f16(tm_s, dql + ko, dkh + ko, idesc_s, 1u);
+            at_umma_f16(tm_s, dqh + ko, dkl + ko, idesc_s, 1u);
+          }
+        }
+        umma_commit(&bar_s);
+      }
+      __syncwarp();
+    }
+    mbar_wait(&bar_s, ph_s);
+    ph_s ^= 1u;
+    tc_fence_after();
+    if (blk + 1 < nblk) issue_k(j0 + AT_BK);      // the K tile is free once S is complete
+    cp_async_commit_();
+    // ---- online softmax over this thread's 32 keys of the block
+    float s[32];
+    at_ld32(tm_s + lane_base + (uint32_t)(32 * half), s);
+    float mb = -INFINITY;
+    const int jb = j0 + 32 * half;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      s[j] = (jb + j < Lk) ? s[j] * qscale : -INFINITY;
+      mb = fmaxf(mb, s[j]);
+    }
+    const float m_new = fmaxf(m_run, mb);
+    float alpha = 1.f;
+    if (m_new == -INFINITY) {          // no valid key for this half so far
+#pragma unroll
+      for (int j = 0; j < 32; ++j) s[j] = 0.f;
+    } else {
+      alpha = exp2f(m_run - m_new);    // exp2(-inf) = 0 on the first valid block
+      float lsum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { s[j] = exp2f(s[j] - m_new); lsum += s[j]; }
+      l_run = l_run * alpha + lsum;
+      m_run = m_new;
+    }
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+      uint4 hi, lo;
+      hi.x = at_split2(s[8 * c8 + 0], s[8 * c8 + 1], lo.x);
+      hi.y = at_split2(s[8 * c8 + 2], s[8 * c8 + 3], lo.y);
+      hi.z = at_split2(s[8 * c8 + 4], s[8 * c8 + 5], lo.z);
+      hi.w = at_split2(s[8 * c8 + 6], s[8 * c8 + 7], lo.w);
+      const uint32_t off = sw128(row, 4 * half + c8);
+      *reinterpret_cast<uint4*>(p_hi + off) = hi;
+      *reinterpret_cast<uint4*>(p_lo + off) = lo;
+    }
+    at_cp_wait<1>();                 // V(blk) has landed (K(blk + 1) may still be in flight)
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- O_blk(half x) = P[:, 32x .. 32x + 32) V[32x .. 32x + 32, :]   (two k-steps per key half)
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t dph = make_desc(smem_u32(p_hi)), dpl = make_desc(smem_u32(p_lo));
+#pragma unroll
+        for (int kk = 0; kk < AT_BK / 16; ++kk) {
+          const uint32_t td = tm_o + (uint32_t)((kk >> 1) * Cf::DP);
+          const uint32_t accf = (kk & 1) ? 1u : 0u;
+          const uint64_t ka = (uint64_t)(2 * kk);
+          uint64_t dvh, dvl;
+          if (VT) {
+            dvh = make_desc(smem_u32(v_hi)) + ka;
+            dvl = make_desc(smem_u32(v_lo)) + ka;
+          } else {
+            dvh = make_desc_mn(smem_u32(v_hi) + (uint32_t)kk * 16u * 128u, AT_BK * 128);
+            dvl = make_desc_mn(smem_u32(v_lo) + (uint32_t)kk * 16u * 128u, AT_BK * 128);
+          }
+          at_umma_f16(td, dph + ka, dvh, idesc_o, accf);
+          at_umma_f16(td, dpl + ka, dvh, idesc_o, 1u);
+          at_umma_f16(td, dph + ka, dvl, idesc_o, 1u);
+        }
+        umma_commit(&bar_o);
+      }
+      __syncwarp();
+    }
+    mbar_wait(&bar_o, ph_o);
+    ph_o ^= 1u;
+    tc_fence_after();
+    if (blk + 1 < nblk) issue_v(j0 + AT_BK);      // the V tile is free once O_blk is complete
+    cp_async_commit_();
+    {
+      float ob[16];
+#pragma unroll
+      for (int c0 = 0; c0 < Cf::DP; c0 += 16) {
+        at_ld16(tm_o + (uint32_t)(half * Cf::DP) + lane_base + (uint32_t)c0, ob);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[c0 + i] = fmaf(acc[c0 + i], alpha, ob[i]);
+      }
+    }
+    tc_fence_before();
+  }
+  at_cp_wait<0>();
+  __syncthreads();                  // all MMAs are complete (bar_o) and every thread has left the loop: the tiles are free
+
+  // ---- merge the two key halves of a row through shared memory, normalise, store
+  float* mw = reinterpret_cast<float*>(smem);              // [128 rows][D + 2]
+  if (half == 1) {
+    float* w = mw + row * (D + 2);
+    w[0] = m_run; w[1] = l_run;
+#pragma unroll
+    for (int c = 0; c < D; ++c) w[2 + c] = acc[c];
+  }
+  __syncthreads();
+  if (half == 0 && q0 + row < Lq) {
+    const float* w = mw + row * (D + 2);
+    const float m1 = w[0], l1 = w[1];
+    const float m = fmaxf(m_run, m1);
+    const float a0 = exp2f(m_run - m);
+    const float a1 = (m1 == -INFINITY) ? 0.f : exp2f(m1 - m);
+    const float inv = 1.f / (l_run * a0 + l1 * a1);
+    const float s0 = a0 * inv, s1 = a1 * inv;
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc[c] = acc[c] * s0 + w[2 + c] * s1;
+    if (phi) {
+      const long base = ((long)n * Lq + q0 + row) * o_pitch + h * D;
+#pragma unroll
+      for (int c = 0; c < D; c += 8) {
+        uint4 hi, lo;
+        hi.x = at_split2(acc[c], acc[c + 1], lo.x); hi.y = at_split2(acc[c + 2], acc[c + 3], lo.y);
+        hi.z = at_split2(acc[c + 4], acc[c + 5], lo.z); hi.w = at_split2(acc[c + 6], acc[c + 7], lo.w);
+        *reinterpret_cast<uint4*>(phi + base + c) = hi;
+        *reinterpret_cast<uint4*>(plo + base + c) = lo;
+      }
+    } else {
+      float* op = o + ((long)n * Lq + q0 + row) * o_pitch + h * D;
+#pragma unroll
+      for (int c = 0; c < D; c += 4)
+        *reinterpret_cast<float4*>(op + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cf::TMEM_COLS) : "memory");
+  }
+}
+
+template <int D, bool VT>
+void launch_ap(const __half* qh, const __half* ql, int q_pitch, const __half* kh, const __half* kl, int k_pitch,
+               const __half* vh, const __half* vl, int v_pitch, float* o, int o_pitch, int N, int heads, int Lq, int Lk,
+               cudaStream_t st, __half* phi, __half* plo) {
+  using Cf = ApCfg<D>;
+  static_assert(2u * Cf::DP * 128u <= Cf::V_BYTES, "transposed V tile does not fit");
+  const size_t smem = Cf::TOTAL + 1024;
+  static bool done[64] = {false};
+  int dev = 0;
+  AGPT_CUDA(cudaGetDevice(&dev));
+  if (!done[dev & 63]) {
+    AGPT_CUDA(cudaFuncSetAttribute(attention_pl_kernel<D, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done[dev & 63] = true;
+  }
+  const float qscale = (1.0f / sqrtf((float)D)) * 1.4426950408889634f;
+  dim3 grid(cdiv(Lq, AT_ROWS), heads, N);
+  attention_pl_kernel<D, VT><<<grid, 256, smem, st>>>(qh, ql, q_pitch, kh, kl, k_pitch, vh, vl, v_pitch, o, o_pitch, Lq, Lk,
+                                                       qscale, phi, plo);
+}
+
 }  // namespace
 
 // returns false when the head dim / alignment is not supported (caller uses the fp32 kernel)
@@ -382,6 +719,42 @@ bool attention_tc(const float* q, int q_pitch, const float* k, int k_pitch, cons
     default: return false;
   }
 #undef AGPT_ATC
+  count_launch(1);
+  AGPT_CUDA(cudaGetLastError());
+  return true;
+}
+
+
+// q / k / v as fp16 hi/lo planes (pitches in elements); returns false when the shape is not supported
+bool attention_planes(const __half* qh, const __half* ql, int q_pitch, const __half* kh, const __half* kl, int k_pitch,
+                      const __half* vh, const __half* vl, int v_pitch, float* o, int o_pitch, int N, int heads, int d,
+                      int Lq, int Lk, cudaStream_t st, __half* phi, __half* plo) {
+  if ((q_pitch | k_pitch | v_pitch) % 8 != 0 || d % 8 != 0 || Lk < 1) return false;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(qh) | reinterpret_cast<uintptr_t>(ql) | reinterpret_cast<uintptr_t>(kh) |
+                       reinterpret_cast<uintptr_t>(kl) | reinterpret_cast<uintptr_t>(vh) | reinterpret_cast<uintptr_t>(vl);
+  if (al & 15) return false;
+  if (phi) {
+    if ((o_pitch % 8) != 0 || ((reinterpret_cast<uintptr_t>(phi) | reinterpret_cast<uintptr_t>(plo)) & 15) != 0) return false;
+  } else if ((o_pitch % 4) != 0 || (reinterpret_cast<uintptr_t>(o) & 15) != 0) {
+    return false;
+  }
+  static int vt = -1;
+  if (vt < 0) { const char* e = getenv("AGPT_ATTN_VT"); vt = (e && e[0] == '1') ? 1 : 0; }
+#define AGPT_APL(D_)                                                                                                     \
+  do {                                                                                                                   \
+    if (vt) launch_ap<D_, true>(qh, ql, q_pitch, kh, kl, k_pitch, vh, vl, v_pitch, o, o_pitch, N, heads, Lq, Lk, st, phi, plo);  \
+    else launch_ap<D_, false>(qh, ql, q_pitch, kh, kl, k_pitch, vh, vl, v_pitch, o, o_pitch, N, heads, Lq, Lk, st, phi, plo);    \
+  } while (0)
+  switch (d) {
+    case 8: AGPT_APL(8); break;
+    case 16: AGPT_APL(16); break;
+    case 32: AGPT_APL(32); break;
+    case 40: AGPT_APL(40); break;
+    case 64: AGPT_APL(64); break;
+    case 80: AGPT_APL(80); break;
+    default: return false;
+  }
+#undef AGPT_APL
   count_launch(1);
   AGPT_CUDA(cudaGetLastError());
   return true;

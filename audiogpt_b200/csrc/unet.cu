@@ -55,7 +55,8 @@ struct Unet : Handle {
 
   // per-call state
   int ctxN = 0, ctxS = 0;
-  DevBuf ctx_kv;
+  DevBuf ctx_kv, ctx_kv_pl;     // hoisted cross-attention K / V of the context: fp32 and fp16 hi/lo planes
+  __half* ctx_hi = nullptr; __half* ctx_lo = nullptr;
   DevBuf arena;
   size_t arena_off = 0, arena_cap = 0;
   DevBuf ddim_eps, ddim_x, ddim_p0;
@@ -88,6 +89,14 @@ struct Unet : Handle {
     P.out = ctx_kv.p; P.out_gstride = 0; P.out_pitch = kv_total;
     P.epi = EPI_BIAS;
     tapconv_launch(P, s);
+    ctx_hi = ctx_lo = nullptr;
+    if (kv_total % 8 == 0) {     // operand planes for the plane-fed attention kernel
+      const size_t n = (size_t)N * S * kv_total, n8 = (n + 7) & ~(size_t)7;
+      ctx_kv_pl.ensure(n8 + 16);
+      ctx_hi = reinterpret_cast<__half*>(ctx_kv_pl.p);
+      ctx_lo = ctx_hi + n8;
+      make_planes(ctx_kv.p, ctx_hi, ctx_lo, (long)n, PRO_NONE, 0.f, s);
+    }
   }
 
   // ---- building blocks --------------------------------------------------------------
@@ -180,19 +189,37 @@ struct Unet : Handle {
     float* a = alloc(rows * C);
     float* qkv = alloc(rows * 3 * C);
     float* ff8 = alloc(rows * 8 * C);
+    static int attn_pl = -1;
+    if (attn_pl < 0) { const char* e = getenv("AGPT_ATTN_PL"); attn_pl = (e && e[0] == '0') ? 0 : 1; }
+    const bool apl = attn_pl && attention_tc_enabled() && ctx_hi && t.dhead % 8 == 0 && C % 8 == 0 &&
+                     (t.dhead == 8 || t.dhead == 16 || t.dhead == 32 || t.dhead == 40 || t.dhead == 64 || t.dhead == 80);
+    Planes pq = apl ? alloc_planes(rows * 3 * C) : Planes{nullptr, nullptr};     // q | k | v planes of the projection GEMMs
     for (size_t bi = 0; bi < t.blocks.size(); ++bi) {
       const XfBlockW& b = t.blocks[bi];
       const bool last = bi + 1 == t.blocks.size();
       layernorm(h, nullptr, b.ln1_g.p, b.ln1_b.p, rows, C, 1e-5f, s, pa.hi, pa.lo);
-      AGPT_CHECK(linear_planes(b.qkv1, pa, C, qkv, 3 * C, rows, EPI_BIAS, nullptr, 0, nullptr, s), "plane-fed GEMM rejected qkv");
-      attention(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, nullptr, C, N, t.heads, t.dhead, HW, HW, s, pt.hi, pt.lo);
+      if (apl) {     // q, k, v leave the projection GEMM as operand planes; the attention kernel copies them into its tiles
+        AGPT_CHECK(linear_planes(b.qkv1, pa, C, nullptr, 3 * C, rows, EPI_BIAS, nullptr, 0, &pq, s), "plane-fed GEMM rejected qkv");
+        AGPT_CHECK(attention_planes(pq.hi, pq.lo, 3 * C, pq.hi + C, pq.lo + C, 3 * C, pq.hi + 2 * C, pq.lo + 2 * C, 3 * C, nullptr, C,
+                                    N, t.heads, t.dhead, HW, HW, s, pt.hi, pt.lo), "plane-fed attention rejected the self-attention");
+      } else {
+        AGPT_CHECK(linear_planes(b.qkv1, pa, C, qkv, 3 * C, rows, EPI_BIAS, nullptr, 0, nullptr, s), "plane-fed GEMM rejected qkv");
+        attention(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, nullptr, C, N, t.heads, t.dhead, HW, HW, s, pt.hi, pt.lo);
+      }
       float* h2 = alloc(rows * C);
       AGPT_CHECK(linear_planes(b.out1, pt, C, h2, C, rows, EPI_RES, h, C, nullptr, s), "plane-fed GEMM rejected attn1.to_out");
       AGPT_CHECK(ctxN == N, "context batch (agpt_unet_set_context) differs from the UNet batch");
       layernorm(h2, nullptr, b.ln2_g.p, b.ln2_b.p, rows, C, 1e-5f, s, pa.hi, pa.lo);
-      AGPT_CHECK(linear_planes(b.q2, pa, C, qkv, C, rows, EPI_BIAS, nullptr, 0, nullptr, s), "plane-fed GEMM rejected attn2.to_q");
-      attention(qkv, C, ctx_kv.p + b.kv_off, kv_total, ctx_kv.p + b.kv_off + C, kv_total, nullptr, C, N, t.heads, t.dhead,
-                HW, ctxS, s, pt.hi, pt.lo);
+      if (apl) {
+        AGPT_CHECK(linear_planes(b.q2, pa, C, nullptr, C, rows, EPI_BIAS, nullptr, 0, &pq, s), "plane-fed GEMM rejected attn2.to_q");
+        AGPT_CHECK(attention_planes(pq.hi, pq.lo, C, ctx_hi + b.kv_off, ctx_lo + b.kv_off, kv_total, ctx_hi + b.kv_off + C,
+                                    ctx_lo + b.kv_off + C, kv_total, nullptr, C, N, t.heads, t.dhead, HW, ctxS, s, pt.hi, pt.lo),
+                   "plane-fed attention rejected the cross-attention");
+      } else {
+        AGPT_CHECK(linear_planes(b.q2, pa, C, qkv, C, rows, EPI_BIAS, nullptr, 0, nullptr, s), "plane-fed GEMM rejected attn2.to_q");
+        attention(qkv, C, ctx_kv.p + b.kv_off, kv_total, ctx_kv.p + b.kv_off + C, kv_total, nullptr, C, N, t.heads, t.dhead,
+                  HW, ctxS, s, pt.hi, pt.lo);
+      }
       float* h3 = alloc(rows * C);
       AGPT_CHECK(linear_planes(b.out2, pt, C, h3, C, rows, EPI_RES, h2, C, nullptr, s), "plane-fed GEMM rejected attn2.to_out");
       // GEGLU feed-forward (attention.py:37-64): ff1 on the plane-fed kernel writes the (a, gate) pairs in fp32, one
@@ -318,7 +345,7 @@ struct Unet : Handle {
     size_t maxc = 0;
     for (auto& r : res) maxc = std::max(maxc, (size_t)std::max(r.cin, r.cout));
     per_res = 5 * hw * maxc;
-    per_st = 26 * hw * maxc;
+    per_st = 30 * hw * maxc;
     const size_t nblocks = in_blocks.size() + out_blocks.size() + 1;
     return (size_t)N * (nblocks * (2 * per_res + per_st + 3 * hw * maxc * 3)) + (1 << 20);
   }

@@ -15,6 +15,9 @@ shapes = [  # name, G, L, Cin, Cout, K, dil, Wreal
     ("unet lin 320", 1, 6240, 320, 320, 1, 1, 0), ("unet ff1", 1, 6240, 320, 2560, 1, 1, 0),
     ("unet ff2", 1, 6240, 1280, 320, 1, 1, 0), ("unet conv 320", 8, 780, 320, 320, 3, 1, 78),
     ("unet conv 640@5x39", 8, 195, 640, 640, 3, 1, 39), ("unet conv 1280->640", 8, 195, 1280, 640, 3, 1, 39),
+    # tap-shift alignment probe: dilation 8 makes every tap's row shift a multiple of the 8-row swizzle atom
+    ("probe k11 d1", 8, 3200, 256, 256, 11, 1, 0), ("probe k11 d8", 8, 3200, 256, 256, 11, 8, 0),
+    ("probe k3 d1 128", 8, 25600, 128, 128, 3, 1, 0), ("probe k3 d8 128", 8, 25600, 128, 128, 3, 8, 0),
 ]
 sel = sys.argv[1:]
 for name, G, Ln, Cin, Cout, K, dil, Wr in shapes:

@@ -230,15 +230,18 @@ def test_tensor_core_attention_vs_fp64(N, heads, d, Lq, Lk):
     vh = kv[:, :, C_:].double().cpu().reshape(N, Lk, heads, d).permute(0, 2, 1, 3)
     ref = (torch.softmax(qh @ kh.transpose(-1, -2) * d ** -0.5, dim=-1) @ vh).permute(0, 2, 1, 3).reshape(N, Lq, C_)
     errs = []
-    for tc in (1, 0):
+    for tc in (1, 2, 0):     # 1: fp32-input tcgen05 kernel, 2: plane-fed tcgen05 kernel (the UNet's), 0: fp32-FMA kernel
         _lib.check(L.agpt_set_attention_tc(tc))
         try:
             o = torch.full((N, Lq, C_), float("nan"), device="cuda")
+            l0 = _lib.launch_count()
             _lib.check(L.agpt_attention(_lib.fptr(q), C_, _lib.fptr(kv), 2 * C_, C.c_void_p(kv.data_ptr() + 4 * C_), 2 * C_,
                                         _lib.fptr(o), C_, N, heads, d, Lq, Lk, _lib.cur_stream()))
             torch.cuda.synchronize()
+            if tc == 2:      # three plane splits + the plane-fed kernel: no silent fall-back to the fp32-input kernel
+                assert _lib.launch_count() - l0 == 4, _lib.launch_count() - l0
         finally:
             _lib.check(L.agpt_set_attention_tc(-1))
         errs.append(rel_rmse(o.cpu(), ref))
-    print(f"attention N={N} h={heads} d={d} {Lq}x{Lk}: rel-RMSE tcgen05 {errs[0]:.2e}  fp32 kernel {errs[1]:.2e}")
-    assert errs[0] < 1e-5 and errs[1] < 1e-5
+    print(f"attention N={N} h={heads} d={d} {Lq}x{Lk}: rel-RMSE tcgen05 {errs[0]:.2e}  plane-fed {errs[1]:.2e}  fp32 kernel {errs[2]:.2e}")
+    assert errs[0] < 1e-5 and errs[1] < 1e-5 and errs[2] < 1e-5
