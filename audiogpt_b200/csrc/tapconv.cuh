@@ -105,6 +105,7 @@ struct PlaneIO {
   int store_f32;                                                                 // also store the fp32 result (residual / accumulator use)
 };
 bool tcconv7_launch(TapConvParams P, const PlaneIO& Q, cudaStream_t st);
+int tc_env_flags();      // AGPT_TC_DBGFLAGS experiment switches (bit 2 = 4: no stacked weight parts)
 void make_planes(const float* x, __half* hi, __half* lo, long n, int pro, float slope, cudaStream_t st);
 
 // ---------------------------------------------------------------- host side

@@ -59,6 +59,11 @@ int tc_get_version() {
   return ver;
 }
 
+int tc_env_flags() {
+  tc_get_version();
+  return g_tc_flags_env;
+}
+
 void tcconv_launch(TapConvParams P, cudaStream_t st) {
   const int ver = tc_get_version();
   P.tc_flags = g_tc_flags_env | P.tc_flags_user;

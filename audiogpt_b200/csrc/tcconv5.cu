@@ -51,6 +51,13 @@ constexpr int V5_THREADS = 320;   // 8 worker warps (0-3, 6-9) + warp 4 (MMA iss
 
 // TMEM allocations are powers of two >= 32 columns
 __host__ __device__ constexpr int tmem_cols(int bn) { return bn <= 32 ? 32 : (bn <= 64 ? 64 : (bn <= 128 ? 128 : 256)); }
+// Stacked weight parts (tiles up to 128 columns): the hi and lo blocks of a weight stage are contiguous rows of one
+// K-major tile, so ONE MMA of width 2 BN computes [A_hi W_hi | A_hi W_lo] into two column ranges of the accumulator
+// and a second of width BN adds A_lo W_hi to the first -- 2 instructions and 20 KB of operand reads per k-step
+// instead of 3 and 24 KB (the MMAs of these kernels are bound by the shared-memory operand fetch: measured
+// ~ (4 KB + 32 B x N) / 100 B per clock and MMA, profiles/r2j_*).  The epilogue adds the two ranges.
+__host__ __device__ constexpr bool tc5_stackable(int bn) { return bn <= 128; }
+__host__ __device__ constexpr int tc5_tmem(int bn) { return tc5_stackable(bn) ? tmem_cols(2 * bn) : tmem_cols(bn); }
 
 template <int BN, int NWK>
 __global__ void __launch_bounds__(NWK == 256 ? V5_THREADS : 192, 1) tcconv5_kernel(const __grid_constant__ TapConvParams P) {
@@ -81,6 +88,7 @@ __global__ void __launch_bounds__(NWK == 256 ? V5_THREADS : 192, 1) tcconv5_kern
   const int nchunks = P.tc_chunks_h, ntaps = P.ntaps, total = nchunks * ntaps;
   const int lo = P.lo_al;
   const bool dbg_on = (P.tc_flags & 2) && P.dbg;
+  const bool stk = tc5_stackable(BN) && !(P.tc_flags & 4);
   long long* dbg = dbg_on ? P.dbg + 8 * ((long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
   if (dbg_on && tid == 0) dbg[0] = clock64();
 
@@ -92,7 +100,7 @@ __global__ void __launch_bounds__(NWK == 256 ? V5_THREADS : 192, 1) tcconv5_kern
   }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)tmem_cols(BN)) : "memory");
+                 ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)tc5_tmem(BN)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (is_worker) {
@@ -230,6 +238,21 @@ __global__ void __launch_bounds__(NWK == 256 ? V5_THREADS : 192, 1) tcconv5_kern
               "=r"(rg[24]), "=r"(rg[25]), "=r"(rg[26]), "=r"(rg[27]), "=r"(rg[28]), "=r"(rg[29]), "=r"(rg[30]), "=r"(rg[31])
             : "r"(taddr) : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (stk) {       // + the A_hi W_lo range
+          uint32_t r2[32];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]),
+                "=r"(r2[8]), "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]), "=r"(r2[14]), "=r"(r2[15]),
+                "=r"(r2[16]), "=r"(r2[17]), "=r"(r2[18]), "=r"(r2[19]), "=r"(r2[20]), "=r"(r2[21]), "=r"(r2[22]), "=r"(r2[23]),
+                "=r"(r2[24]), "=r"(r2[25]), "=r"(r2[26]), "=r"(r2[27]), "=r"(r2[28]), "=r"(r2[29]), "=r"(r2[30]), "=r"(r2[31])
+              : "r"(taddr + (uint32_t)BN) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rg[i] = __float_as_uint(__uint_as_float(rg[i]) + __uint_as_float(r2[i]));
+        }
 #pragma unroll
         for (int qd = 0; qd < 8; ++qd)
           *reinterpret_cast<float4*>(stg + sw128(myrow, qd)) =
@@ -258,6 +281,7 @@ __global__ void __launch_bounds__(NWK == 256 ? V5_THREADS : 192, 1) tcconv5_kern
     {
       // kind::f16: D = F32 (bit 4), A = B = F16 (format 0), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
       const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * BN > 256 ? BN : 2 * BN) >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
       long long dbg_wa = 0, dbg_ww = 0;
       int it = 0;
       for (int c = 0; c < nchunks; ++c) {
@@ -282,9 +306,14 @@ __global__ void __launch_bounds__(NWK == 256 ? V5_THREADS : 192, 1) tcconv5_kern
           if (elect_one()) {
             for (int k = 0; k < ksteps; ++k) {
               const uint64_t ko = (uint64_t)((k * 32) >> 4);
-              umma_f16(tmem_base, dah + ko, dwh + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
-              umma_f16(tmem_base, dal + ko, dwh + ko, idesc, 1u);
-              umma_f16(tmem_base, dah + ko, dwl + ko, idesc, 1u);
+              if (stk) {
+                umma_f16(tmem_base, dah + ko, dwh + ko, idesc2, (it > 0 || k > 0) ? 1u : 0u);   // [hi x hi | hi x lo]
+                umma_f16(tmem_base, dal + ko, dwh + ko, idesc, 1u);                              // += lo x hi
+              } else {
+                umma_f16(tmem_base, dah + ko, dwh + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                umma_f16(tmem_base, dal + ko, dwh + ko, idesc, 1u);
+                umma_f16(tmem_base, dah + ko, dwl + ko, idesc, 1u);
+              }
             }
             umma_commit(&w_empty[s]);
             if (t == ntaps - 1) {
@@ -314,7 +343,7 @@ __global__ void __launch_bounds__(NWK == 256 ? V5_THREADS : 192, 1) tcconv5_kern
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols(BN)) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tc5_tmem(BN)) : "memory");
   }
 }
 

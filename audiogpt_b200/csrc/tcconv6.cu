@@ -65,6 +65,24 @@ __device__ __forceinline__ TileId6 tile_of6(int t, int nct, int nrt) {
 }
 
 // NI = register-prefetched 8-channel items per transform thread (rows r0, r0+32, ...): covers RRA <= 32 * NI
+// accumulate 32 more fp32 TMEM columns of this lane into rg (the A_hi x W_lo range of a stacked accumulator)
+__device__ __forceinline__ void tc6_ld32_add(uint32_t taddr, uint32_t* rg) {
+  uint32_t r2[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]),
+        "=r"(r2[8]), "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]), "=r"(r2[14]), "=r"(r2[15]),
+        "=r"(r2[16]), "=r"(r2[17]), "=r"(r2[18]), "=r"(r2[19]), "=r"(r2[20]), "=r"(r2[21]), "=r"(r2[22]), "=r"(r2[23]),
+        "=r"(r2[24]), "=r"(r2[25]), "=r"(r2[26]), "=r"(r2[27]), "=r"(r2[28]), "=r"(r2[29]), "=r"(r2[30]), "=r"(r2[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) rg[i] = __float_as_uint(__uint_as_float(rg[i]) + __uint_as_float(r2[i]));
+}
+
+
 template <int BN, int NI, bool NARROW>
 __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_constant__ TapConvParams P,
                                                                 const __grid_constant__ CUtensorMap tm_res,
@@ -94,7 +112,14 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
   const int nct = (P.Cout + BN - 1) / BN, nrt = (Lv + TC_ROWS - 1) / TC_ROWS;
   const int ntiles = nct * nrt * P.G;
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;    // two accumulators
+  // Two accumulators.  Tiles up to 128 columns use STACKED weight parts: one MMA of width 2 BN reads the hi and lo
+  // blocks of a weight stage as one tile and leaves [A_hi W_hi | A_hi W_lo] in two column ranges, a second of
+  // width BN adds A_lo W_hi -- 2 instructions / 20 KB of operand reads per k-step instead of 3 / 24 KB; the epilogue
+  // adds the ranges (tcconv5.cu has the measurement behind it).
+  constexpr bool STK = BN <= 128;
+  constexpr uint32_t ACCW = STK ? 2 * BN : BN;                   // accumulator stride in TMEM columns
+  constexpr uint32_t TMEM_COLS = (2 * ACCW < 32) ? 32 : 2 * ACCW;
+  const bool stk = STK && !(P.tc_flags & 4);
 
   if (tid == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], V6_NT); mbar_init(&a_empty[i], 1); }
@@ -244,6 +269,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
     // cycles of dependent single-warp code) is paid once per 12-48 MMAs even on the narrow layers.
     {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | ((uint32_t)((STK ? 2 * BN : BN) >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
       const uint64_t DC = make_desc(0);                         // descriptor constants; the low 14 bits take (address >> 4)
       const uint32_t a16 = smem_u32(smem + S.a_hi[0]) >> 4;     // operand ring: hi tiles, then lo tiles
       const uint32_t abuf16 = (uint32_t)(RRA * 128) >> 4;       // one hi (or lo) tile
@@ -256,7 +282,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
       for (int tl = 0; tl < my_tiles; ++tl) {
         const int acc = tl & 1, na = tl >> 1;
         if (na >= 1) { DBG_WAIT6(3, mbar_wait(&acc_empty[acc], (uint32_t)((na - 1) & 1))); tc_fence_after(); }
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * ACCW;
         uint32_t nz = 0;                                        // 0 for the very first MMA of the tile
         for (int c = 0; c < nchunks; ++c, ++gc) {
           const int buf = gc % NA;
@@ -279,10 +305,16 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
                 const uint64_t dwl = dwh + wlo16;
                 for (int k = 0; k < ksteps; ++k) {
                   const uint64_t ko = (uint64_t)(2 * k);        // 32 bytes per k-step
-                  umma_f16(tmem_d, dah + ko, dwh + ko, idesc, nz);
-                  nz = 1u;
-                  umma_f16(tmem_d, dal + ko, dwh + ko, idesc, 1u);
-                  umma_f16(tmem_d, dah + ko, dwl + ko, idesc, 1u);
+                  if (stk) {
+                    umma_f16(tmem_d, dah + ko, dwh + ko, idesc2, nz);      // [hi x hi | hi x lo]
+                    nz = 1u;
+                    umma_f16(tmem_d, dal + ko, dwh + ko, idesc, 1u);       // += lo x hi
+                  } else {
+                    umma_f16(tmem_d, dah + ko, dwh + ko, idesc, nz);
+                    nz = 1u;
+                    umma_f16(tmem_d, dal + ko, dwh + ko, idesc, 1u);
+                    umma_f16(tmem_d, dah + ko, dwl + ko, idesc, 1u);
+                  }
                 }
               }
               umma_commit(&w_empty[s]);
@@ -395,7 +427,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
           t_epi0 = dbg_on ? clock64() : 0;
         }
         uint32_t rg[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + cb);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * ACCW + (uint32_t)cb;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -406,6 +438,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
               "=r"(rg[24]), "=r"(rg[25]), "=r"(rg[26]), "=r"(rg[27]), "=r"(rg[28]), "=r"(rg[29]), "=r"(rg[30]), "=r"(rg[31])
             : "r"(taddr) : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (stk) tc6_ld32_add(taddr + (uint32_t)BN, rg);
         if (cb + 32 >= BN) {                      // last TMEM read of this accumulator: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(&acc_empty[acc]);
@@ -528,7 +561,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
 #pragma unroll 1
       for (int cb = 0; cb < BN; cb += 32) {
         uint32_t rg[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + cb);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * ACCW + (uint32_t)cb;
         const long long t_ld0 = dbg_on ? clock64() : 0;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -540,6 +573,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
               "=r"(rg[24]), "=r"(rg[25]), "=r"(rg[26]), "=r"(rg[27]), "=r"(rg[28]), "=r"(rg[29]), "=r"(rg[30]), "=r"(rg[31])
             : "r"(taddr) : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (stk) tc6_ld32_add(taddr + (uint32_t)BN, rg);
         if (dbg_on) dbgacc[4] += clock64() - t_ld0;
         if (cb + 32 >= BN) {                      // last TMEM read of this accumulator: hand it back to the MMA warp
           tc_fence_before();

@@ -93,6 +93,24 @@ __device__ __forceinline__ float pro_scalar(int pro, float slope, float v) {
   return v;
 }
 
+// accumulate 32 more fp32 TMEM columns of this lane into rg (the A_hi x W_lo range of a stacked accumulator)
+__device__ __forceinline__ void tc7_ld32_add(uint32_t taddr, uint32_t* rg) {
+  uint32_t r2[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]),
+        "=r"(r2[8]), "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]), "=r"(r2[14]), "=r"(r2[15]),
+        "=r"(r2[16]), "=r"(r2[17]), "=r"(r2[18]), "=r"(r2[19]), "=r"(r2[20]), "=r"(r2[21]), "=r"(r2[22]), "=r"(r2[23]),
+        "=r"(r2[24]), "=r"(r2[25]), "=r"(r2[26]), "=r"(r2[27]), "=r"(r2[28]), "=r"(r2[29]), "=r"(r2[30]), "=r"(r2[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) rg[i] = __float_as_uint(__uint_as_float(rg[i]) + __uint_as_float(r2[i]));
+}
+
+
 template <int BN>
 __global__ void __launch_bounds__(V7_THREADS, 1)
 tcconv7_kernel(const __grid_constant__ TapConvParams P, const __grid_constant__ PlaneIO Q,
@@ -122,7 +140,10 @@ tcconv7_kernel(const __grid_constant__ TapConvParams P, const __grid_constant__ 
   const int nct = (P.Cout + BN - 1) / BN, nrt = (P.L + TC_ROWS - 1) / TC_ROWS;
   const int ntiles = nct * nrt * P.G;
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  // two accumulators of stacked weight parts ([A_hi W_hi | A_hi W_lo] by one MMA of width 2 BN, + A_lo W_hi: tcconv6.cu)
+  constexpr uint32_t ACCW = 2 * BN;
+  constexpr uint32_t TMEM_COLS = (2 * ACCW < 32) ? 32 : 2 * ACCW;
+  const bool stk = !(P.tc_flags & 4);
 
   if (tid == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
@@ -163,6 +184,7 @@ tcconv7_kernel(const __grid_constant__ TapConvParams P, const __grid_constant__ 
   } else if (warp == 4) {
     // =========================== MMA issuer (as tcconv6) ===========================
     const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
     const uint64_t DC = make_desc(0);
     const uint32_t a16 = smem_u32(smem + S.a_hi[0]) >> 4;
     const uint32_t abuf16 = (uint32_t)(RRA * 128) >> 4;
@@ -175,7 +197,7 @@ tcconv7_kernel(const __grid_constant__ TapConvParams P, const __grid_constant__ 
     for (int tl = 0; tl < my_tiles; ++tl) {
       const int acc = tl & 1, na = tl >> 1;
       if (na >= 1) { mbar_wait(&acc_empty[acc], (uint32_t)((na - 1) & 1)); tc_fence_after(); }
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      const uint32_t tmem_d = tmem_base + (uint32_t)acc * ACCW;
       uint32_t nz = 0;
       for (int c = 0; c < nchunks; ++c, ++gc) {
         const int buf = gc % NA;
@@ -198,10 +220,16 @@ tcconv7_kernel(const __grid_constant__ TapConvParams P, const __grid_constant__ 
               const uint64_t dwl = dwh + wlo16;
               for (int k = 0; k < ksteps; ++k) {
                 const uint64_t ko = (uint64_t)(2 * k);
-                umma_f16(tmem_d, dah + ko, dwh + ko, idesc, nz);
-                nz = 1u;
-                umma_f16(tmem_d, dal + ko, dwh + ko, idesc, 1u);
-                umma_f16(tmem_d, dah + ko, dwl + ko, idesc, 1u);
+                if (stk) {
+                  umma_f16(tmem_d, dah + ko, dwh + ko, idesc2, nz);        // [hi x hi | hi x lo]
+                  nz = 1u;
+                  umma_f16(tmem_d, dal + ko, dwh + ko, idesc, 1u);         // += lo x hi
+                } else {
+                  umma_f16(tmem_d, dah + ko, dwh + ko, idesc, nz);
+                  nz = 1u;
+                  umma_f16(tmem_d, dal + ko, dwh + ko, idesc, 1u);
+                  umma_f16(tmem_d, dah + ko, dwl + ko, idesc, 1u);
+                }
               }
             }
             umma_commit(&w_empty[s]);
@@ -295,7 +323,7 @@ tcconv7_kernel(const __grid_constant__ TapConvParams P, const __grid_constant__ 
           acc_ready = true;
         }
         uint32_t rg[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + cb);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * ACCW + (uint32_t)cb;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -306,6 +334,7 @@ tcconv7_kernel(const __grid_constant__ TapConvParams P, const __grid_constant__ 
               "=r"(rg[24]), "=r"(rg[25]), "=r"(rg[26]), "=r"(rg[27]), "=r"(rg[28]), "=r"(rg[29]), "=r"(rg[30]), "=r"(rg[31])
             : "r"(taddr) : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (stk) tc7_ld32_add(taddr + (uint32_t)BN, rg);
         if (cb + 32 >= BN) {
           tc_fence_before();
           mbar_arrive(&acc_empty[acc]);
@@ -411,6 +440,7 @@ void make_planes(const float* x, __half* hi, __half* lo, long n, int pro, float 
 // Launch (1-D layers, bias / residual / accumulate / relu-type epilogues).  Returns false when the layer does not
 // qualify; the caller then uses tcconv6 on the fp32 tensor.
 bool tcconv7_launch(TapConvParams P, const PlaneIO& Q, cudaStream_t st) {
+  P.tc_flags = tc_env_flags() | P.tc_flags_user;
   if (!P.w_h || P.Wreal != 0 || !Q.in_hi || !Q.in_lo) return false;
   const bool epi_ok = P.epi == EPI_BIAS || P.epi == EPI_RES || P.epi == EPI_ACC || P.epi == EPI_RELU || P.epi == EPI_ADDVEC ||
                       P.epi == EPI_TANH || P.epi == EPI_MISH || P.epi == EPI_SILU;
