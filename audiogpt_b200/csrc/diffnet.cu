@@ -251,23 +251,17 @@ struct Diffnet : Handle {
       const unsigned eg = (unsigned)std::min<long>(cdivl(n, 256), 4736);
       addvec_planes_kernel<<<eg, 256, 0, st>>>(xcur.p, dprojv, dproj_gs, gs, C, xh, xl, n);
       count_launch(1);
-      static int fuse_gate = -1, fuse_out = -1;
-      if (fuse_gate < 0) { const char* e = getenv("AGPT_DIFFNET_FUSE_GATE"); fuse_gate = (e && e[0] == '0') ? 0 : 1; }
-      if (fuse_out < 0) { const char* e = getenv("AGPT_DIFFNET_FUSE_OUT"); fuse_out = (e && e[0] == '0') ? 0 : 1; }
-      const bool fuse_o = fuse_out && C % outp[0].tc_bn == 0 && (dproj_gs % 4) == 0 && C % 4 == 0;   // whole column tiles on either side of the split
-      // gh != nullptr: the gate (net.py:72-74) runs in the GEMM's epilogue and only the planes of z leave the kernel
       auto gemm = [&](const PackedConv& pc, int dilv, const __half* ih, const __half* il, float* outp_, const float* res_,
-                      long res_gs, int res_pitch, __half* gh, __half* gl) {
+                      long res_gs, int res_pitch) {
         TapConvParams P = tapconv_params(pc, B, T, 0, dilv);
         P.in = nullptr; P.in_gstride = gs; P.in_pitch = C;
         P.out = outp_; P.out_gstride = (long)T * 2 * C; P.out_pitch = 2 * C;
-        P.pro = PRO_NONE; P.epi = gh ? EPI_GATE : (res_ ? EPI_RES : EPI_BIAS);
+        P.pro = PRO_NONE; P.epi = res_ ? EPI_RES : EPI_BIAS;
         P.res = res_; P.res_gstride = res_gs; P.res_pitch = res_pitch;
         PlaneIO Q;
         memset(&Q, 0, sizeof(Q));
         Q.in_hi = ih; Q.in_lo = il; Q.in_gstride = gs; Q.in_pitch = C;
-        Q.store_f32 = gh ? 0 : 1;
-        if (gh) { Q.out_hi = gh; Q.out_lo = gl; Q.outp_pitch = C; Q.outp_gstride = gs; Q.out_pro = PRO_NONE; }
+        Q.store_f32 = 1;
         const double r = (double)rows;
         void* rec = profile_begin(P, true, 4.0 * (r * C + r * 2 * C * (res_ ? 2 : 1) + (double)pc.ntaps * C * 2 * C), st);
         AGPT_CHECK(tcconv7_launch(P, Q, st), "plane-fed kernel rejected a DiffNet layer");
@@ -277,41 +271,13 @@ struct Diffnet : Handle {
       for (int l = 0; l < L; ++l) {
         const int d = 1 << (l % cfg.dilation_cycle_length);
         // y = dilated_conv(x + dproj) + conditioner_projection(cond)     (net.py:67-71; the conditioner is the TMA-loaded residual)
-        if (fuse_gate) {
-          gemm(dil[l], d, xh, xl, nullptr, condp.p + (long)l * 2 * C, (long)T * L * 2 * C, L * 2 * C, zh, zl);
-        } else {
-          gemm(dil[l], d, xh, xl, ybuf.p, condp.p + (long)l * 2 * C, (long)T * L * 2 * C, L * 2 * C, nullptr, nullptr);
-          gate_planes_kernel<<<eg, 256, 0, st>>>(ybuf.p, zh, zl, n / 2);
-          count_launch(1);
-        }
+        gemm(dil[l], d, xh, xl, ybuf.p, condp.p + (long)l * 2 * C, (long)T * L * 2 * C, L * 2 * C);
+        gate_planes_kernel<<<eg, 256, 0, st>>>(ybuf.p, zh, zl, n / 2);
+        gemm(outp[l], 1, zh, zl, obuf.p, nullptr, 0, 0);
         const bool last = l + 1 == L;
-        if (fuse_o) {
-          // output_projection with the residual / skip update and the next layer's operand planes in its epilogue
-          TapConvParams P = tapconv_params(outp[l], B, T, 0, 1);
-          P.in = nullptr; P.in_gstride = gs; P.in_pitch = C;
-          P.pro = PRO_NONE; P.epi = EPI_DIFFOUT; P.csplit = C; P.accumulate = (l > 0);
-          P.out = xcur.p; P.out_gstride = gs; P.out_pitch = C;
-          P.res = xcur.p; P.res_gstride = gs; P.res_pitch = C;
-          P.out2 = skip.p; P.out2_gstride = gs; P.out2_pitch = C;
-          PlaneIO Q;
-          memset(&Q, 0, sizeof(Q));
-          Q.in_hi = zh; Q.in_lo = zl; Q.in_gstride = gs; Q.in_pitch = C;
-          Q.store_f32 = 1;
-          if (!last) {
-            Q.out_hi = xh; Q.out_lo = xl; Q.outp_pitch = C; Q.outp_gstride = gs; Q.out_pro = PRO_NONE;
-            Q.out_vec = dprojv + (long)(l + 1) * C; Q.out_vec_gs = dproj_gs;
-          }
-          const double r = (double)rows;
-          void* rec = profile_begin(P, true, 4.0 * (r * C + r * C * 4 + (double)C * 2 * C), st);
-          AGPT_CHECK(tcconv7_launch(P, Q, st), "plane-fed kernel rejected a DiffNet output projection");
-          profile_end(rec, st);
-          count_launch(1);
-        } else {
-          gemm(outp[l], 1, zh, zl, obuf.p, nullptr, 0, 0, nullptr, nullptr);
-          diffout_planes_kernel<<<eg, 256, 0, st>>>(obuf.p, xcur.p, skip.p, l > 0 ? 1 : 0, last ? dprojv : dprojv + (long)(l + 1) * C, dproj_gs, gs, C,
-                                                    last ? nullptr : xh, last ? nullptr : xl, n);
-          count_launch(1);
-        }
+        diffout_planes_kernel<<<eg, 256, 0, st>>>(obuf.p, xcur.p, skip.p, l > 0 ? 1 : 0, last ? dprojv : dprojv + (long)(l + 1) * C, dproj_gs, gs, C,
+                                                  last ? nullptr : xh, last ? nullptr : xl, n);
+        count_launch(2);
       }
       AGPT_CUDA(cudaGetLastError());
     } else

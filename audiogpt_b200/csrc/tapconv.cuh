@@ -103,7 +103,6 @@ struct PlaneIO {
   __half* out_hi; __half* out_lo; long outp_gstride; int outp_pitch;             // planes to emit (nullptr: none)
   int out_pro; float out_slope;                                                  // consumer prologue applied before the split
   int store_f32;                                                                 // also store the fp32 result (residual / accumulator use)
-  const float* out_vec; long out_vec_gs;                                         // per-channel vector added before the planes are split (row g)
 };
 bool tcconv7_launch(TapConvParams P, const PlaneIO& Q, cudaStream_t st);
 int tc_env_flags();      // AGPT_TC_DBGFLAGS experiment switches (bit 2 = 4: no stacked weight parts)

@@ -116,8 +116,7 @@ __global__ void __launch_bounds__(V7_THREADS, 1)
 tcconv7_kernel(const __grid_constant__ TapConvParams P, const __grid_constant__ PlaneIO Q,
                const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
                const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_out,
-               const __grid_constant__ CUtensorMap tm_phi, const __grid_constant__ CUtensorMap tm_plo,
-               const __grid_constant__ CUtensorMap tm_out2) {
+               const __grid_constant__ CUtensorMap tm_phi, const __grid_constant__ CUtensorMap tm_plo) {
   extern __shared__ uint8_t smem_raw_[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
   const int RRA = P.R, NA = P.tc_na, NW = P.tc_nw, NB = P.tc_nb, tps = P.tc_tps;
@@ -267,12 +266,8 @@ tcconv7_kernel(const __grid_constant__ TapConvParams P, const __grid_constant__ 
     // =========================== epilogue warps (whole-block TMA boxes) ===========================
     const int quad = warp;
     const int LA = NB - 2;
-    const bool gate = P.epi == EPI_GATE;      // (gate, filter) column pairs -> sigmoid(g) * tanh(f): planes of Cout / 2 channels
-    // EPI_DIFFOUT (net.py:76-78): column tiles below csplit update x in place, x <- (x + v) / sqrt(2) (x is the TMA-loaded
-    // residual and the fp32 output) and emit the planes of x + out_vec; tiles from csplit on (+)= into the skip sum (tm_out2)
-    const bool diffout = P.epi == EPI_DIFFOUT;
-    const bool has_res = (P.epi == EPI_RES || P.epi == EPI_ACC || P.epi == EPI_GATE || diffout) && P.res != nullptr;
-    const bool red_add = (P.epi == EPI_ACC || diffout) && P.accumulate;
+    const bool has_res = (P.epi == EPI_RES || P.epi == EPI_ACC) && P.res != nullptr;
+    const bool red_add = (P.epi == EPI_ACC) && P.accumulate;
     const bool f32_out = Q.store_f32 != 0;
     const bool leader = tid == 0;
     float* cvs = reinterpret_cast<float*>(smem + S.cvs) + quad * 256;
@@ -283,13 +278,11 @@ tcconv7_kernel(const __grid_constant__ TapConvParams P, const __grid_constant__ 
       const int tl = m / nblk, b = m - tl * nblk;
       const TileId7 T = tile_of7((int)blockIdx.x + tl * (int)gridDim.x, nct, nrt);
       const int bi = m % NB;
-      if (diffout && T.ct * BN >= P.csplit) { mbar_arrive(&e_full[bi]); return; }     // skip tile: nothing to load, keep the phase count
       mbar_arrive_expect_tx(&e_full[bi], 16384u);
       tma_load_3d(smem + S.stg + bi * V7_EBLK, &tm_res, T.ct * BN + 32 * b, T.q0, T.g, &e_full[bi]);
     };
     if (leader) {
       if (f32_out) tma_prefetch_desc(&tm_out);
-      if (diffout) tma_prefetch_desc(&tm_out2);
       if (planes) { tma_prefetch_desc(&tm_phi); tma_prefetch_desc(&tm_plo); }
       if (has_res) {
         tma_prefetch_desc(&tm_res);
@@ -301,8 +294,6 @@ tcconv7_kernel(const __grid_constant__ TapConvParams P, const __grid_constant__ 
       const TileId7 T = tile_of7((int)blockIdx.x + tl * (int)gridDim.x, nct, nrt);
       const int acc = tl & 1;
       const int co0 = T.ct * BN;
-      const bool tile_x = !diffout || co0 < P.csplit;          // false: a skip tile of EPI_DIFFOUT
-      const bool tile_pl = planes && tile_x;
       __syncwarp();
       for (int c = lane; c < BN; c += 32) {
         const int co = co0 + c;
@@ -351,15 +342,14 @@ tcconv7_kernel(const __grid_constant__ TapConvParams P, const __grid_constant__ 
         if (has_res) mbar_wait(&e_full[bi], (uint32_t)((j / NB) & 1));
         const uint32_t buf_sh = smem_u32(smem + S.stg + bi * V7_EBLK + quad * 4096);
         const uint32_t cvs_sh = smem_u32(cvs + cb);
-        // hi block, lo at + V7_PBLK; rows of 64 B (32 channels), 32 B for the 16 gated channels of a block
-        const uint32_t pl_sh = smem_u32(smem + S.pl + (j & 1) * 2 * V7_PBLK + quad * (gate ? 1024 : 2048));
+        const uint32_t pl_sh = smem_u32(smem + S.pl + (j & 1) * 2 * V7_PBLK + quad * 2048);   // hi block, lo at + V7_PBLK
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           float4 rr[4], cc[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int qd = 4 * hh + i;
-            rr[i] = (has_res && tile_x) ? lds128(buf_sh + sw128(lane, qd)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            rr[i] = has_res ? lds128(buf_sh + sw128(lane, qd)) : make_float4(0.f, 0.f, 0.f, 0.f);
             cc[i] = lds128(cvs_sh + 16u * (uint32_t)qd);
           }
           uint32_t hi[8], lw[8];
@@ -375,34 +365,17 @@ tcconv7_kernel(const __grid_constant__ TapConvParams P, const __grid_constant__ 
               case EPI_TANH: v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); break;
               case EPI_MISH: v.x = mishf_(v.x); v.y = mishf_(v.y); v.z = mishf_(v.z); v.w = mishf_(v.w); break;
               case EPI_SILU: v.x = siluf_(v.x); v.y = siluf_(v.y); v.z = siluf_(v.z); v.w = siluf_(v.w); break;
-              case EPI_DIFFOUT:
-                if (tile_x) {
-                  const float r2 = 0.70710678118654752440f;
-                  v.x *= r2; v.y *= r2; v.z *= r2; v.w *= r2;
-                }
-                break;
               default: break;
             }
             if (f32_out) sts128(buf_sh + sw128(lane, qd), v);
-            if (gate) {        // net.py:72-74 on the interleaved pairs (g0, f0, g1, f1)
-              hi[i] = split2(sigmoidf_(v.x) * tanhf(v.y), sigmoidf_(v.z) * tanhf(v.w), lw[i]);
-            } else if (tile_pl) {     // NOTE: a layer that accumulates (red_add) cannot emit planes of the final sum
-              float4 pv = v;
-              if (Q.out_vec) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(Q.out_vec + (long)T.g * Q.out_vec_gs + co0 + cb + 4 * qd));
-                pv.x += a.x; pv.y += a.y; pv.z += a.z; pv.w += a.w;
-              }
-              const float p0 = pro_scalar(Q.out_pro, Q.out_slope, pv.x), p1 = pro_scalar(Q.out_pro, Q.out_slope, pv.y);
-              const float p2 = pro_scalar(Q.out_pro, Q.out_slope, pv.z), p3 = pro_scalar(Q.out_pro, Q.out_slope, pv.w);
+            if (planes) {      // NOTE: a layer that accumulates (red_add) cannot emit planes of the final sum
+              const float p0 = pro_scalar(Q.out_pro, Q.out_slope, v.x), p1 = pro_scalar(Q.out_pro, Q.out_slope, v.y);
+              const float p2 = pro_scalar(Q.out_pro, Q.out_slope, v.z), p3 = pro_scalar(Q.out_pro, Q.out_slope, v.w);
               hi[2 * i] = split2(p0, p1, lw[2 * i]);
               hi[2 * i + 1] = split2(p2, p3, lw[2 * i + 1]);
             }
           }
-          if (gate) {          // this lane's row: 8 gated channels of this half = 16 bytes per plane (row pitch 32 B)
-            const uint32_t ro = pl_sh + (uint32_t)lane * 32u + (uint32_t)hh * 16u;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ro), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ro + V7_PBLK), "r"(lw[0]), "r"(lw[1]), "r"(lw[2]), "r"(lw[3]) : "memory");
-          } else if (tile_pl) {       // this lane's row: 16 fp16 of this half = 32 bytes per plane (row pitch 64 B, no swizzle)
+          if (planes) {        // this lane's row: 16 fp16 of this half = 32 bytes per plane (row pitch 64 B, no swizzle)
             const uint32_t ro = pl_sh + (uint32_t)lane * 64u + (uint32_t)hh * 32u;
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ro), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ro + 16u), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
@@ -415,21 +388,13 @@ tcconv7_kernel(const __grid_constant__ TapConvParams P, const __grid_constant__ 
         if (leader) {
           if (f32_out) {
             const uint8_t* blk = smem + S.stg + bi * V7_EBLK;
-            if (diffout) {
-              if (tile_x) tma_store_3d(&tm_out, co0 + cb, T.q0, T.g, blk);
-              else if (red_add) tma_reduce_add_3d(&tm_out2, co0 + cb - P.csplit, T.q0, T.g, blk);
-              else tma_store_3d(&tm_out2, co0 + cb - P.csplit, T.q0, T.g, blk);
-            } else if (red_add) {
-              tma_reduce_add_3d(&tm_out, co0 + cb, T.q0, T.g, blk);
-            } else {
-              tma_store_3d(&tm_out, co0 + cb, T.q0, T.g, blk);
-            }
+            if (red_add) tma_reduce_add_3d(&tm_out, co0 + cb, T.q0, T.g, blk);
+            else tma_store_3d(&tm_out, co0 + cb, T.q0, T.g, blk);
           }
-          if (tile_pl) {
+          if (planes) {
             const uint8_t* pb = smem + S.pl + (j & 1) * 2 * V7_PBLK;
-            const int pc0 = gate ? (co0 + cb) / 2 : co0 + cb;
-            tma_store_3d(&tm_phi, pc0, T.q0, T.g, pb);
-            tma_store_3d(&tm_plo, pc0, T.q0, T.g, pb + V7_PBLK);
+            tma_store_3d(&tm_phi, co0 + cb, T.q0, T.g, pb);
+            tma_store_3d(&tm_plo, co0 + cb, T.q0, T.g, pb + V7_PBLK);
           }
           tma_commit_group();
         }
@@ -478,13 +443,8 @@ bool tcconv7_launch(TapConvParams P, const PlaneIO& Q, cudaStream_t st) {
   P.tc_flags = tc_env_flags() | P.tc_flags_user;
   if (!P.w_h || P.Wreal != 0 || !Q.in_hi || !Q.in_lo) return false;
   const bool epi_ok = P.epi == EPI_BIAS || P.epi == EPI_RES || P.epi == EPI_ACC || P.epi == EPI_RELU || P.epi == EPI_ADDVEC ||
-                      P.epi == EPI_TANH || P.epi == EPI_MISH || P.epi == EPI_SILU ||
-                      (P.epi == EPI_GATE && Q.out_hi && !Q.store_f32 && P.Cout % 2 == 0) ||     // gated planes only
-                      (P.epi == EPI_DIFFOUT && Q.store_f32 && P.out && P.out2 && P.res == P.out && P.csplit > 0 &&
-                       P.csplit % P.tc_bn == 0 && P.csplit < P.Cout);
+                      P.epi == EPI_TANH || P.epi == EPI_MISH || P.epi == EPI_SILU;
   if (!epi_ok) return false;
-  const bool diffout = P.epi == EPI_DIFFOUT;
-  if (Q.out_vec && ((reinterpret_cast<uintptr_t>(Q.out_vec) & 15) != 0 || (Q.out_vec_gs % 4) != 0)) return false;
   int lo = P.tap_off[0], hi = P.tap_off[0];
   for (int t = 1; t < P.ntaps; ++t) { lo = std::min(lo, P.tap_off[t]); hi = std::max(hi, P.tap_off[t]); }
   P.lo_al = lo;
@@ -493,21 +453,18 @@ bool tcconv7_launch(TapConvParams P, const PlaneIO& Q, cudaStream_t st) {
   P.R = RRA;
   const int BN = P.tc_bn;
   const bool planes = Q.out_hi != nullptr;
-  const bool gate = P.epi == EPI_GATE;
-  const bool has_res = (P.epi == EPI_RES || P.epi == EPI_ACC || gate || diffout) && P.res != nullptr;
+  const bool has_res = (P.epi == EPI_RES || P.epi == EPI_ACC) && P.res != nullptr;
   if (planes && P.epi == EPI_ACC && P.accumulate) return false;
-  CUtensorMap tm_ahi, tm_alo, tm_res, tm_out, tm_phi, tm_plo, tm_out2;
-  memset(&tm_res, 0, sizeof(tm_res)); memset(&tm_out, 0, sizeof(tm_out)); memset(&tm_out2, 0, sizeof(tm_out2));
+  CUtensorMap tm_ahi, tm_alo, tm_res, tm_out, tm_phi, tm_plo;
+  memset(&tm_res, 0, sizeof(tm_res)); memset(&tm_out, 0, sizeof(tm_out));
   memset(&tm_phi, 0, sizeof(tm_phi)); memset(&tm_plo, 0, sizeof(tm_plo));
   bool ok = tma_encode_plane(&tm_ahi, Q.in_hi, P.Cin, P.L, P.G, Q.in_pitch, Q.in_gstride, H_KCH, RRA, true) &&
             tma_encode_plane(&tm_alo, Q.in_lo, P.Cin, P.L, P.G, Q.in_pitch, Q.in_gstride, H_KCH, RRA, true);
-  const int cx = diffout ? P.csplit : P.Cout;       // channels of the in-place tensor
-  if (ok && Q.store_f32) ok = tma_encode_rows(&tm_out, P.out, cx, P.L, P.G, P.out_pitch, P.out_gstride, 128);
-  if (ok && has_res) ok = tma_encode_rows(&tm_res, P.res, cx, P.L, P.G, P.res_pitch, P.res_gstride, 128);
-  if (ok && diffout) ok = tma_encode_rows(&tm_out2, P.out2, P.Cout - P.csplit, P.L, P.G, P.out2_pitch, P.out2_gstride, 128);
+  if (ok && Q.store_f32) ok = tma_encode_rows(&tm_out, P.out, P.Cout, P.L, P.G, P.out_pitch, P.out_gstride, 128);
+  if (ok && has_res) ok = tma_encode_rows(&tm_res, P.res, P.Cout, P.L, P.G, P.res_pitch, P.res_gstride, 128);
   if (ok && planes)
-    ok = tma_encode_plane(&tm_phi, Q.out_hi, gate ? P.Cout / 2 : cx, P.L, P.G, Q.outp_pitch, Q.outp_gstride, gate ? 16 : 32, 128, false) &&
-         tma_encode_plane(&tm_plo, Q.out_lo, gate ? P.Cout / 2 : cx, P.L, P.G, Q.outp_pitch, Q.outp_gstride, gate ? 16 : 32, 128, false);
+    ok = tma_encode_plane(&tm_phi, Q.out_hi, P.Cout, P.L, P.G, Q.outp_pitch, Q.outp_gstride, 32, 128, false) &&
+         tma_encode_plane(&tm_plo, Q.out_lo, P.Cout, P.L, P.G, Q.outp_pitch, Q.outp_gstride, 32, 128, false);
   if (!ok) return false;
   const int tps = std::max(1, std::min(P.ntaps, (int)(32768 / (2L * BN * 128))));
   P.tc_tps = tps;
@@ -544,9 +501,9 @@ bool tcconv7_launch(TapConvParams P, const PlaneIO& Q, cudaStream_t st) {
     attr_done = true;
   }
   const int grid = std::min(ntiles, sms);
-  if (BN == 128) tcconv7_kernel<128><<<grid, V7_THREADS, smem, st>>>(P, Q, tm_ahi, tm_alo, tm_res, tm_out, tm_phi, tm_plo, tm_out2);
-  else if (BN == 64) tcconv7_kernel<64><<<grid, V7_THREADS, smem, st>>>(P, Q, tm_ahi, tm_alo, tm_res, tm_out, tm_phi, tm_plo, tm_out2);
-  else if (BN == 32) tcconv7_kernel<32><<<grid, V7_THREADS, smem, st>>>(P, Q, tm_ahi, tm_alo, tm_res, tm_out, tm_phi, tm_plo, tm_out2);
+  if (BN == 128) tcconv7_kernel<128><<<grid, V7_THREADS, smem, st>>>(P, Q, tm_ahi, tm_alo, tm_res, tm_out, tm_phi, tm_plo);
+  else if (BN == 64) tcconv7_kernel<64><<<grid, V7_THREADS, smem, st>>>(P, Q, tm_ahi, tm_alo, tm_res, tm_out, tm_phi, tm_plo);
+  else if (BN == 32) tcconv7_kernel<32><<<grid, V7_THREADS, smem, st>>>(P, Q, tm_ahi, tm_alo, tm_res, tm_out, tm_phi, tm_plo);
   else return false;
   return true;
 }
