@@ -439,6 +439,7 @@ __global__ void __launch_bounds__(256, ApCfg<D>::MINB) attention_pl_kernel(
   // the tiles start as zeros: padding channels (d .. 64) are never written again, rows past Lk keep finite data
   for (uint32_t i = tid; i < Cf::TOTAL / 16; i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
+  pdl_wait();          // the zero fill and the TMEM allocation overlap the previous kernel's tail
 
   const __half* kbh = kh + ((long)n * Lk) * k_pitch + h * D;
   const __half* kbl = kl + ((long)n * Lk) * k_pitch + h * D;
@@ -695,8 +696,8 @@ void launch_ap(const __half* qh, const __half* ql, int q_pitch, const __half* kh
   }
   const float qscale = (1.0f / sqrtf((float)D)) * 1.4426950408889634f;
   dim3 grid(cdiv(Lq, AT_ROWS), heads, N);
-  attention_pl_kernel<D, VT><<<grid, 256, smem, st>>>(qh, ql, q_pitch, kh, kl, k_pitch, vh, vl, v_pitch, o, o_pitch, Lq, Lk,
-                                                       qscale, phi, plo);
+  launch_pdl(attention_pl_kernel<D, VT>, grid, dim3(256), smem, st, qh, ql, q_pitch, kh, kl, k_pitch, vh, vl, v_pitch, o, o_pitch, Lq, Lk,
+             qscale, phi, plo);
 }
 
 }  // namespace

@@ -56,6 +56,7 @@ __global__ void diff_step_embed_dev_kernel(float* __restrict__ out, const int* _
 __global__ void p_sample_tab_kernel(float* __restrict__ x, const float* __restrict__ eps, const float* const* __restrict__ noises_pp,
                                     long noise_stride, const float* __restrict__ coef_tab, const int* __restrict__ ctr,
                                     int nsteps, int clip, long n) {
+  pdl_wait();
   const int k = *ctr;
   const float* coef = coef_tab + 5 * (long)k;
   const float A = coef[0], Bc = coef[1], c1 = coef[2], c2 = coef[3], s = coef[4];
@@ -80,6 +81,7 @@ __device__ __forceinline__ void dn_split(float v, __half& hi, __half& lo) {
 // planes of x[b][t][c] + vec[b][c]   (net.py:67: y = x + diffusion_projection(step)); vec_gs = 0: one row for all samples
 __global__ void addvec_planes_kernel(const float* __restrict__ x, const float* __restrict__ vec, int vec_gs, long per_sample, int C,
                                      __half* __restrict__ phi, __half* __restrict__ plo, long total) {
+  pdl_wait();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long b = i / per_sample;
     const int c = (int)(i % C);
@@ -88,6 +90,7 @@ __global__ void addvec_planes_kernel(const float* __restrict__ x, const float* _
 }
 // y [rows][2C] with (gate, filter) pairs interleaved -> planes of sigmoid(gate) * tanh(filter) [rows][C]   (net.py:72-74)
 __global__ void gate_planes_kernel(const float* __restrict__ y, __half* __restrict__ phi, __half* __restrict__ plo, long n2) {
+  pdl_wait();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long)gridDim.x * blockDim.x) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(y) + i);     // (g0, f0, g1, f1)
     const float o0 = sigmoidf_(v.x) * tanhf(v.y), o1 = sigmoidf_(v.z) * tanhf(v.w);
@@ -102,6 +105,7 @@ __global__ void gate_planes_kernel(const float* __restrict__ y, __half* __restri
 __global__ void diffout_planes_kernel(const float* __restrict__ o, float* __restrict__ x, float* __restrict__ skip, int accumulate,
                                       const float* __restrict__ vec_next, int vec_gs, long per_sample, int C,
                                       __half* __restrict__ phi, __half* __restrict__ plo, long total) {
+  pdl_wait();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long row = i / C;
     const int c = (int)(i - row * C);
@@ -249,7 +253,7 @@ struct Diffnet : Handle {
       __half* xh = reinterpret_cast<__half*>(plx.p); __half* xl = xh + n;
       __half* zh = reinterpret_cast<__half*>(plz.p); __half* zl = zh + n;
       const unsigned eg = (unsigned)std::min<long>(cdivl(n, 256), 4736);
-      addvec_planes_kernel<<<eg, 256, 0, st>>>(xcur.p, dprojv, dproj_gs, gs, C, xh, xl, n);
+      launch_pdl(addvec_planes_kernel, dim3(eg), dim3(256), 0, st, xcur.p, dprojv, dproj_gs, gs, C, xh, xl, n);
       count_launch(1);
       auto gemm = [&](const PackedConv& pc, int dilv, const __half* ih, const __half* il, float* outp_, const float* res_,
                       long res_gs, int res_pitch) {
@@ -272,11 +276,11 @@ struct Diffnet : Handle {
         const int d = 1 << (l % cfg.dilation_cycle_length);
         // y = dilated_conv(x + dproj) + conditioner_projection(cond)     (net.py:67-71; the conditioner is the TMA-loaded residual)
         gemm(dil[l], d, xh, xl, ybuf.p, condp.p + (long)l * 2 * C, (long)T * L * 2 * C, L * 2 * C);
-        gate_planes_kernel<<<eg, 256, 0, st>>>(ybuf.p, zh, zl, n / 2);
+        launch_pdl(gate_planes_kernel, dim3(eg), dim3(256), 0, st, ybuf.p, zh, zl, n / 2);
         gemm(outp[l], 1, zh, zl, obuf.p, nullptr, 0, 0);
         const bool last = l + 1 == L;
-        diffout_planes_kernel<<<eg, 256, 0, st>>>(obuf.p, xcur.p, skip.p, l > 0 ? 1 : 0, last ? dprojv : dprojv + (long)(l + 1) * C, dproj_gs, gs, C,
-                                                  last ? nullptr : xh, last ? nullptr : xl, n);
+        launch_pdl(diffout_planes_kernel, dim3(eg), dim3(256), 0, st, obuf.p, xcur.p, skip.p, l > 0 ? 1 : 0, last ? dprojv : dprojv + (long)(l + 1) * C, dproj_gs, gs, C,
+                   last ? nullptr : xh, last ? nullptr : xl, n);
         count_launch(2);
       }
       AGPT_CUDA(cudaGetLastError());
@@ -430,7 +434,7 @@ void gd_sample_loop(Handle* hh, float* x_io, int t_hi, int t_lo, const float* co
     select_row(h->dproj_table.p, ctr, h->dproj_cur.p, L * C, s);
     h->eps_core(xl, h->dproj_cur.p, 0, h->loop_eps.p, s);
     dim3 grid((unsigned)std::min<long>(cdivl(n, 256), 1184), B);
-    p_sample_tab_kernel<<<grid, 256, 0, s>>>(xl, h->loop_eps.p, noise_pp, noise_stride, h->coef_table.p, ctr, nsteps, clip, n);
+    launch_pdl(p_sample_tab_kernel, grid, dim3(256), 0, s, xl, h->loop_eps.p, noise_pp, noise_stride, h->coef_table.p, ctr, nsteps, clip, n);
     count_launch(1);
     AGPT_CUDA(cudaGetLastError());
     step_inc(ctr, s);

@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(NWK == 256 ? V5_THREADS : 192, 1) tcconv5_kern
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // everything above overlaps the previous kernel's tail
   if (dbg_on && tid == 0) dbg[1] = clock64();
 
   if (is_worker) {
@@ -442,12 +443,12 @@ static bool tcconv5_try(TapConvParams P, int BN, cudaStream_t st) {
     AGPT_CUDA(cudaFuncSetAttribute(tcconv5_kernel<32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
     attr_done_dev[dev & 63] = true;
   }
-  if (BN == 256) tcconv5_kernel<256, 256><<<grid, nthreads, smem, st>>>(P);
-  else if (BN == 128) tcconv5_kernel<128, 256><<<grid, nthreads, smem, st>>>(P);
-  else if (BN == 96) tcconv5_kernel<96, 256><<<grid, nthreads, smem, st>>>(P);
-  else if (BN == 64) tcconv5_kernel<64, 256><<<grid, nthreads, smem, st>>>(P);
-  else if (P.tc_nwk == 128) tcconv5_kernel<32, 128><<<grid, nthreads, smem, st>>>(P);
-  else tcconv5_kernel<32, 256><<<grid, nthreads, smem, st>>>(P);
+  if (BN == 256) launch_pdl(tcconv5_kernel<256, 256>, grid, dim3(nthreads), smem, st, P);
+  else if (BN == 128) launch_pdl(tcconv5_kernel<128, 256>, grid, dim3(nthreads), smem, st, P);
+  else if (BN == 96) launch_pdl(tcconv5_kernel<96, 256>, grid, dim3(nthreads), smem, st, P);
+  else if (BN == 64) launch_pdl(tcconv5_kernel<64, 256>, grid, dim3(nthreads), smem, st, P);
+  else if (P.tc_nwk == 128) launch_pdl(tcconv5_kernel<32, 128>, grid, dim3(nthreads), smem, st, P);
+  else launch_pdl(tcconv5_kernel<32, 256>, grid, dim3(nthreads), smem, st, P);
   return true;
 }
 

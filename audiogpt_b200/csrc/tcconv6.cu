@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // everything above overlaps the previous kernel's tail
   // optional per-CTA wait accounting (tc_flags & 2): [0] total, [1] MMA wait a_full, [2] MMA wait w_full,
   // [3] MMA wait acc_empty, [4] transform wait a_empty, [5] epilogue wait acc_full, [6] epilogue busy, [7] producer wait
   const bool dbg_on = (P.tc_flags & 2) && P.dbg;
@@ -622,12 +623,12 @@ static void launch6(const TapConvParams& P, const CUtensorMap& tr, const CUtenso
                     cudaStream_t st) {
   const int NI = cdiv(RRA, 32);
   if (BN == 32 && P.Cin <= 32 && RRA <= 192) {   // narrow layers: 64 rows per pass, two register sets in flight
-    tcconv6_kernel<(BN == 32 ? 32 : 64), 3, true><<<grid, V6_THREADS, smem, st>>>(P, tr, to);
+    launch_pdl(tcconv6_kernel<(BN == 32 ? 32 : 64), 3, true>, dim3(grid), dim3(V6_THREADS), smem, st, P, tr, to);
     return;
   }
-  if (NI <= 5) tcconv6_kernel<BN, 5, false><<<grid, V6_THREADS, smem, st>>>(P, tr, to);
-  else if (NI <= 6) tcconv6_kernel<BN, 6, false><<<grid, V6_THREADS, smem, st>>>(P, tr, to);
-  else tcconv6_kernel<BN, 10, false><<<grid, V6_THREADS, smem, st>>>(P, tr, to);
+  if (NI <= 5) launch_pdl(tcconv6_kernel<BN, 5, false>, dim3(grid), dim3(V6_THREADS), smem, st, P, tr, to);
+  else if (NI <= 6) launch_pdl(tcconv6_kernel<BN, 6, false>, dim3(grid), dim3(V6_THREADS), smem, st, P, tr, to);
+  else launch_pdl(tcconv6_kernel<BN, 10, false>, dim3(grid), dim3(V6_THREADS), smem, st, P, tr, to);
 }
 template <int BN>
 static void attrs6() {

@@ -161,6 +161,7 @@ tcconv7_kernel(const __grid_constant__ TapConvParams P, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // everything above overlaps the previous kernel's tail
 
   if (warp == 6) {
     // =========================== activation producer (TMA) ===========================
@@ -501,9 +502,9 @@ bool tcconv7_launch(TapConvParams P, const PlaneIO& Q, cudaStream_t st) {
     attr_done = true;
   }
   const int grid = std::min(ntiles, sms);
-  if (BN == 128) tcconv7_kernel<128><<<grid, V7_THREADS, smem, st>>>(P, Q, tm_ahi, tm_alo, tm_res, tm_out, tm_phi, tm_plo);
-  else if (BN == 64) tcconv7_kernel<64><<<grid, V7_THREADS, smem, st>>>(P, Q, tm_ahi, tm_alo, tm_res, tm_out, tm_phi, tm_plo);
-  else if (BN == 32) tcconv7_kernel<32><<<grid, V7_THREADS, smem, st>>>(P, Q, tm_ahi, tm_alo, tm_res, tm_out, tm_phi, tm_plo);
+  if (BN == 128) launch_pdl(tcconv7_kernel<128>, dim3(grid), dim3(V7_THREADS), smem, st, P, Q, tm_ahi, tm_alo, tm_res, tm_out, tm_phi, tm_plo);
+  else if (BN == 64) launch_pdl(tcconv7_kernel<64>, dim3(grid), dim3(V7_THREADS), smem, st, P, Q, tm_ahi, tm_alo, tm_res, tm_out, tm_phi, tm_plo);
+  else if (BN == 32) launch_pdl(tcconv7_kernel<32>, dim3(grid), dim3(V7_THREADS), smem, st, P, Q, tm_ahi, tm_alo, tm_res, tm_out, tm_phi, tm_plo);
   else return false;
   return true;
 }
