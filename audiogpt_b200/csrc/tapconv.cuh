@@ -134,7 +134,7 @@ void tcconv_launch(TapConvParams P, cudaStream_t st);          // tcgen05 dispat
 bool tcconv5_launch(TapConvParams P, cudaStream_t st);
 bool tcconv6_launch(TapConvParams P, cudaStream_t st, bool force);
 struct HTile { int bn; const float* w; long ntiles; };
-HTile pick_h_tile(const TapConvParams& P, int sms, bool with96 = true);   // tile width for the fp16 kernels (tcconv5.cu); 96 exists in tcconv5 only
+HTile pick_h_tile(const TapConvParams& P, int sms, bool with96 = true, bool with256 = true);   // tile width for the fp16 kernels (tcconv5.cu): tcconv6 has no 96, tcconv7 no 256
 void pack_h_weights(struct PackedConv& pc, const std::vector<float>& h);
 bool tcconv_supported(const TapConvParams& P);
 void pack_tc_weights(struct PackedConv& pc, const std::vector<float>& h);

@@ -455,7 +455,7 @@ static bool tcconv5_try(TapConvParams P, int BN, cudaStream_t st) {
 // Tile width: the candidate (256 / native 128|64|32 / 96 and 64 for native-128 layers) with the smallest
 // waves x per-tile cost, where waves = ceil(tiles / SMs).  Per-tile cost relative to BN = 128 from the
 // micro-benchmarks (profiles/r1e_*): wider tiles amortise the activation operand, narrower ones fill the SMs.
-HTile pick_h_tile(const TapConvParams& P, int sms, bool with96) {
+HTile pick_h_tile(const TapConvParams& P, int sms, bool with96, bool with256) {
   static int allow256 = -1;
   if (allow256 < 0) { const char* e = getenv("AGPT_TC_BN256"); allow256 = (e && e[0] == '0') ? 0 : 1; }
   const int Lv = tc_lv(P);
@@ -471,7 +471,7 @@ HTile pick_h_tile(const TapConvParams& P, int sms, bool with96) {
     const double sc = (double)cdiv(nt, (long)sms) * cost(bn);
     if (sc < bs - 1e-9) { bs = sc; best = HTile{bn, w, nt}; }
   };
-  if (allow256) consider(256, P.w_h256);
+  if (allow256 && with256) consider(256, P.w_h256);
   if (P.tc_bn == 128) consider(64, P.w_h64);
   if (P.tc_bn == 128 && allow96 && with96) consider(96, P.w_h96);   // e.g. 640 channels on 16 row tiles: 112 tiles in one wave
   return best;

@@ -142,7 +142,7 @@ tcconv7_kernel(const __grid_constant__ TapConvParams P, const __grid_constant__ 
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   // two accumulators of stacked weight parts ([A_hi W_hi | A_hi W_lo] by one MMA of width 2 BN, + A_lo W_hi: tcconv6.cu)
   constexpr uint32_t ACCW = 2 * BN;
-  constexpr uint32_t TMEM_COLS = (2 * ACCW < 32) ? 32 : 2 * ACCW;
+  constexpr uint32_t TMEM_COLS = (2 * ACCW <= 32) ? 32 : (2 * ACCW <= 64 ? 64 : (2 * ACCW <= 128 ? 128 : (2 * ACCW <= 256 ? 256 : 512)));   // power of two
   const bool stk = !(P.tc_flags & 4);
 
   if (tid == 0) {
@@ -452,6 +452,17 @@ bool tcconv7_launch(TapConvParams P, const PlaneIO& Q, cudaStream_t st) {
   const int RRA = round_up(TC_ROWS + (hi - lo), 8);
   if (RRA > 256) return false;                       // one tensor-map box per part (boxDim <= 256)
   P.R = RRA;
+  int dev = 0, sms = 148;
+  AGPT_CUDA(cudaGetDevice(&dev));
+  AGPT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  // tile width: a narrower image of a native-128 layer when 128-wide tiles would leave SMs idle (the UNet's GEMMs on
+  // 1 560 rows: 640 columns -> 130 tiles of 64 instead of 65 of 128)
+  static int pick7 = -1;
+  if (pick7 < 0) { const char* e = getenv("AGPT_TC7_PICK"); pick7 = (e && e[0] == '0') ? 0 : 1; }
+  if (pick7 && P.strips == 0) {
+    const HTile c = pick_h_tile(P, sms, true, false);
+    if (c.bn != P.tc_bn && c.w && (c.bn == 64 || c.bn == 96)) { P.w_h = c.w; P.tc_bn = c.bn; }
+  }
   const int BN = P.tc_bn;
   const bool planes = Q.out_hi != nullptr;
   const bool has_res = (P.epi == EPI_RES || P.epi == EPI_ACC) && P.res != nullptr;
@@ -491,18 +502,17 @@ bool tcconv7_launch(TapConvParams P, const PlaneIO& Q, cudaStream_t st) {
   const size_t smem = (size_t)S.total + 1024;
   if (smem > (size_t)kMaxDyn7) return false;
   const int ntiles = cdiv(P.L, TC_ROWS) * cdiv(P.Cout, BN) * P.G;
-  int dev = 0, sms = 148;
-  AGPT_CUDA(cudaGetDevice(&dev));
-  AGPT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   static bool attr_done = false;
   if (!attr_done) {
     AGPT_CUDA(cudaFuncSetAttribute(tcconv7_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn7));
+    AGPT_CUDA(cudaFuncSetAttribute(tcconv7_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn7));
     AGPT_CUDA(cudaFuncSetAttribute(tcconv7_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn7));
     AGPT_CUDA(cudaFuncSetAttribute(tcconv7_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn7));
     attr_done = true;
   }
   const int grid = std::min(ntiles, sms);
   if (BN == 128) launch_pdl(tcconv7_kernel<128>, dim3(grid), dim3(V7_THREADS), smem, st, P, Q, tm_ahi, tm_alo, tm_res, tm_out, tm_phi, tm_plo);
+  else if (BN == 96) launch_pdl(tcconv7_kernel<96>, dim3(grid), dim3(V7_THREADS), smem, st, P, Q, tm_ahi, tm_alo, tm_res, tm_out, tm_phi, tm_plo);
   else if (BN == 64) launch_pdl(tcconv7_kernel<64>, dim3(grid), dim3(V7_THREADS), smem, st, P, Q, tm_ahi, tm_alo, tm_res, tm_out, tm_phi, tm_plo);
   else if (BN == 32) launch_pdl(tcconv7_kernel<32>, dim3(grid), dim3(V7_THREADS), smem, st, P, Q, tm_ahi, tm_alo, tm_res, tm_out, tm_phi, tm_plo);
   else return false;

@@ -101,6 +101,24 @@ def test_tcgen05_schedules_match_fma(ver):
         _lib.check(L.agpt_set_tc_version(-1))
 
 
+def test_plane_fed_kernel_matches_fma():
+    """Schedule selector 8 runs the layer on the plane-fed kernel (tcconv7: TMA-fed fp16 hi/lo operand planes in, fp32 result
+    + planes of the result out) against the fp32-FMA kernel; 1-D layers only.  The 1 560-row shapes take the 64- and
+    96-wide tiles the launcher picks when 128-wide tiles would leave SMs idle (last column tile partial at 96)."""
+    L = _lib.lib()
+    torch.zeros(1).cuda()
+    _lib.check(L.agpt_set_tc_version(8))
+    try:
+        for G, Ln, Cin, Cout, K, dil, Wr in [(2, 3000, 256, 256, 11, 5, 0), (16, 400, 256, 512, 3, 2, 0), (1, 1560, 640, 640, 1, 1, 0),
+                                             (1, 1560, 640, 1920, 1, 1, 0), (1, 6240, 320, 320, 1, 1, 0), (2, 500, 96, 40, 5, 2, 0)]:
+            for epi_res in (0, 1):
+                rel = (C.c_double * 2)()
+                _lib.check(L.agpt_check_tapconv(G, Ln, Cin, Cout, K, dil, Wr, epi_res, C.c_double(1.0), C.c_double(1.0), rel))
+                assert rel[0] < 2e-4 and rel[1] < 2e-5, (G, Ln, Cin, Cout, K, dil, epi_res, rel[0], rel[1])
+    finally:
+        _lib.check(L.agpt_set_tc_version(-1))
+
+
 @pytest.mark.parametrize("x_scale,w_spread,tol_max,tol_rms", [
     (1e-4, 1.0, 4e-4, 4e-5),      # tiny activations: the lo part of |x| < 2^-3 is an fp16 subnormal (absolute floor 2^-25)
     (1e-2, 1.0, 2e-4, 2e-5),
