@@ -6,6 +6,8 @@ import torch
 from audiogpt_b200 import _lib, specs
 L = _lib.lib()
 bad = 0
+mode = int(sys.argv[1]) if len(sys.argv) > 1 else 1      # 1: fp32-input kernel, 2: plane-fed kernel
+_lib.check(L.agpt_set_attention_tc(mode))
 for N, heads, d, Lq, Lk in [(1, 2, 40, 130, 77), (1, 2, 80, 70, 130), (1, 1, 8, 5, 3), (1, 2, 64, 129, 64)]:
     Cc = heads * d
     q = specs.synth_tensor((N, Lq, Cc), seed=1).cuda()
@@ -21,5 +23,5 @@ for N, heads, d, Lq, Lk in [(1, 2, 40, 130, 77), (1, 2, 80, 70, 130), (1, 1, 8, 
     e = ((o.double().cpu() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
     ok = e < 1e-5
     bad += 0 if ok else 1
-    print(f"attention_tc h={heads} d={d} {Lq}x{Lk}: rel-RMSE {e:.2e} {'ok' if ok else 'FAIL'}", flush=True)
+    print(f"attention mode {mode} h={heads} d={d} {Lq}x{Lk}: rel-RMSE {e:.2e} {'ok' if ok else 'FAIL'}", flush=True)
 sys.exit(1 if bad else 0)

@@ -10,6 +10,10 @@ SHAPES = [(2, 3000, 256, 256, 11, 5, 0), (2, 5000, 128, 128, 3, 3, 0), (2, 9000,
           (2, 195, 640, 640, 3, 1, 39), (1, 130, 1280, 320, 1, 1, 0), (2, 4, 64, 96, 3, 1, 0),
           (2, 300, 80, 256, 7, 1, 0), (1, 780, 4, 320, 3, 1, 78), (2, 500, 96, 40, 5, 2, 0)]
 ver = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+if ver == 8:     # plane-fed kernel: 1-D layers; the 1 560-row shapes take the 64- / 96-wide tiles
+    SHAPES = [s for s in SHAPES if s[6] == 0] + [(1, 1560, 640, 640, 1, 1, 0), (1, 1560, 640, 1920, 1, 1, 0), (8, 195, 640, 640, 3, 1, 0)]
+else:
+    SHAPES = SHAPES + [(8, 195, 640, 640, 3, 1, 39)]     # the 96-wide tile of the one-tile-per-CTA kernel
 L = _lib.lib()
 torch.zeros(1).cuda()
 _lib.check(L.agpt_set_tc_version(ver))
