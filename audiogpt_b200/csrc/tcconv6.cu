@@ -341,8 +341,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) tcconv6_kernel(const __grid_con
         for (int c = 0; c < nchunks; ++c) {
           for (int t0 = 0; t0 < ntaps; t0 += tps, ++it) {
             const int s = it % NW, n = it / NW;
-            uint32_t bytes = (uint32_t)(min(ntaps, t0 + tps) - t0) * tapbytes;
-            if (P.tc_flags & 8) bytes >>= 1;      // timing experiment only (wrong results): half the weight traffic
+            const uint32_t bytes = (uint32_t)(min(ntaps, t0 + tps) - t0) * tapbytes;
             if (n >= 1) DBG_WAIT6(7, mbar_wait(&w_empty[s], (uint32_t)((n - 1) & 1)));
             mbar_arrive_expect_tx(&w_full[s], bytes);
             bulk_g2s(smem + S.w[s], wsrc + (size_t)(c * ntaps + t0) * tapbytes, bytes, &w_full[s]);
