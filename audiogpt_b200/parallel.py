@@ -154,12 +154,23 @@ class P2PGather:
         fn, args = reduce_tensor(self.buf)
         handles = [None] * self.world
         dist.all_gather_object(handles, args)
-        self.peers = []
-        for r in range(self.world):
-            self.peers.append(self.buf if r == self.rank else fn(*handles[r]))
+        self.peers, err = [], None
+        try:
+            for r in range(self.world):
+                self.peers.append(self.buf if r == self.rank else fn(*handles[r]))
+            probe = torch.zeros(1, dtype=dtype, device=self.dev)
+            for r in range(self.world):                # one element to every peer: mapping and peer access really work
+                self.peers[r][0, self.rank].reshape(-1)[:1].copy_(probe)
+            torch.cuda.synchronize(self.dev)
+        except Exception as e:                         # noqa: BLE001 -- reported below, on every rank together
+            err = e
+        # every rank learns whether ALL mappings succeeded (instead of a barrier a failed rank would never reach)
+        flag = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            raise RuntimeError(f"P2PGather: mapping the peers' buffers failed on at least one rank (this rank: {err!r})")
         self.stream = torch.cuda.Stream(device=self.dev)
         self.n = 0
-        dist.barrier()
 
     def submit(self, x: torch.Tensor):
         slot = self.n % self.slots

@@ -424,7 +424,11 @@ def run_ours(args):
     gather, gather_kind = None, None
     if n_gpus > 1:
         if os.environ.get("AGPT_GATHER", "p2p") == "p2p":
-            gather, gather_kind = parallel.P2PGather((B_PER_GPU, 1, T_FRAMES * HOP), device=dev), "p2p_copy_engine"
+            try:
+                gather, gather_kind = parallel.P2PGather((B_PER_GPU, 1, T_FRAMES * HOP), device=dev), "p2p_copy_engine"
+            except RuntimeError as e:        # raised on every rank together (peer mapping unavailable): NCCL path instead
+                print(f"[bench] {e}; using the NCCL gather", file=sys.stderr)
+                gather, gather_kind = parallel.AsyncGather(), "nccl_async (p2p mapping failed)"
         else:
             gather, gather_kind = parallel.AsyncGather(), "nccl_async"
 

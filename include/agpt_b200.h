@@ -50,7 +50,8 @@ int agpt_set_tc_version(int v);
  * CrossAttention.forward (ldm/modules/attention.py:170-193): q [N][Lq][q_pitch], k / v [N][Lk][pitch] device rows with
  * head h at channels [h*d, (h+1)*d); o [N][Lq][o_pitch].  Default: QK^T and PV on the tcgen05 tensor cores
  * (error-compensated fp16 parts, fp32 accumulation, exact online softmax; d in {8,16,32,40,64,80});
- * agpt_set_attention_tc(0) / AGPT_ATTN_TC=0 selects the fp32-FMA kernel.                                        */
+ * agpt_set_attention_tc(0) / AGPT_ATTN_TC=0 selects the fp32-FMA kernel, (2) / =2 routes the call through the
+ * plane-fed kernel the UNet uses internally (q / k / v split into fp16 hi/lo planes first; test / A-B route).      */
 int agpt_attention(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, float* o,
                    int o_pitch, int N, int heads, int d, int Lq, int Lk, void* stream);
 int agpt_set_attention_tc(int on);
