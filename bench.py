@@ -195,6 +195,8 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if os.environ.get("AGPT_REF_CUDA_INIT") == "1" and torch.cuda.is_available():    # diagnostic: process state of the GPU arm
+        torch.zeros(1).cuda()
     if args.workload == "ddim":
         rate, sps, cores = cpu_ddim_rate(max(2, min(args.steps, 6)))
         sample = (f"B=1: {max(2, min(args.steps, 6))} of the {DDIM_S} DDIM steps (2 UNet forwards each, CFG) on {cores} threads; "
