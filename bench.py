@@ -134,6 +134,27 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU arms
+_ALLOC_NOTE = ""
+
+
+def _cpu_allocator_tuning():
+    """The CPU forward allocates and frees 50-MB intermediates; with glibc's defaults every one of them is mmap'ed,
+    page-faulted and unmapped again, which on a 128-CPU box costs the 16-thread CPU path 5x (measured: 473 -> 2 500
+    frames/s, profiles/r2s_reference_arm.txt).  Keep freed memory in the heap instead (what MALLOC_MMAP_MAX_=0
+    MALLOC_TRIM_THRESHOLD_=... would do from the environment): the CPU arms get their best."""
+    global _ALLOC_NOTE
+    if _ALLOC_NOTE:
+        return
+    try:
+        import ctypes
+        libc = ctypes.CDLL("libc.so.6")
+        M_TRIM_THRESHOLD, M_TOP_PAD, M_MMAP_MAX = -1, -2, -4
+        ok = libc.mallopt(M_MMAP_MAX, 0) and libc.mallopt(M_TRIM_THRESHOLD, 2**31 - 1) and libc.mallopt(M_TOP_PAD, 1 << 30)
+        _ALLOC_NOTE = "glibc mallopt(M_MMAP_MAX=0, M_TRIM_THRESHOLD=2 GiB, M_TOP_PAD=1 GiB)" if ok else "glibc defaults (mallopt refused)"
+    except Exception as e:                      # noqa: BLE001
+        _ALLOC_NOTE = f"glibc defaults ({e!r})"
+
+
 def _calibrate_threads(fn):
     """torch's intra-op pool scales badly past a few dozen threads on these convs (and torchrun pins
     OMP_NUM_THREADS=1): time a short sample at several thread counts and keep the best."""
@@ -157,6 +178,7 @@ def cpu_vocode_rate(steps, warmup, batch, frames):
     """frames/s of the CPU oracle (the reference's forward restated on torch fp32 CPU ops)."""
     from audiogpt_b200 import specs
     from oracle import hifigan_ref as hr
+    _cpu_allocator_tuning()
     h = specs.HIFIGAN_V1
     sd = specs.synth_hifigan(h, 1234)
     cal = specs.synth_tensor((1, 80, 200), seed=1, scale=2.0, shift=-4.0)
@@ -177,6 +199,7 @@ def cpu_ddim_rate(n_steps_sample):
     """clips/s of the CPU oracle DDIM-100 + CFG chain at B = 1, from a bounded sample of its 100 steps."""
     from audiogpt_b200 import specs
     from oracle import ldm_ref as lr
+    _cpu_allocator_tuning()
     cfg = specs.UNET_TXT2AUDIO
     sd = specs.synth_unet(cfg, 4040)
     tab = lr.ldm_schedule()
@@ -213,7 +236,7 @@ def run_reference_arm(args):
     # reference would run them; the RATE is the result, ms_per_step is the sample's own (not extrapolated)
     sb = 2
     rate, sec, cores = cpu_vocode_rate(args.steps, max(1, min(args.warmup, 2)), sb, T_FRAMES)
-    sample = f"{sb} of {B_PER_GPU} utterances x {T_FRAMES} frames per step ({sb * T_FRAMES} frames), {args.steps} steps, {cores} threads"
+    sample = f"{sb} of {B_PER_GPU} utterances x {T_FRAMES} frames per step ({sb * T_FRAMES} frames), {args.steps} steps, {cores} threads; {_ALLOC_NOTE}"
     ddim_rate, ddim_sps, ddim_cores = cpu_ddim_rate(3)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "frames_per_step": sb * T_FRAMES,
@@ -573,7 +596,7 @@ def run_ours(args):
         cpu_baseline = {"value": cb_rate, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"2 of {B_PER_GPU} utterances x {T_FRAMES} frames in one forward call, 1 warm-up + 3 timed passes of "
                                   f"oracle/hifigan_ref.py on {cores} threads (best of a thread-count calibration; "
-                                  f"box has {os.cpu_count()} logical CPUs)"}
+                                  f"box has {os.cpu_count()} logical CPUs); {_ALLOC_NOTE}"}
         if ddim and "error" not in ddim:
             r, sps, dcores = cpu_ddim_rate(3)
             ddim["cpu_baseline"] = {"value": r, "unit": DDIM_UNIT, "cores": dcores, "kind": "port",
