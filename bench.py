@@ -327,6 +327,11 @@ def measure_ddim(dev, rank, n_gpus, chains, peaks, want_cpu, keep=None):
     value = clips / (ms_chain * 1e-3)
     ach = DDIM_TFLOP_PER_CLIP * B / (ms_chain * 1e-3)             # per GPU, algorithmic
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+    ddim_traffic = None
+    try:      # DRAM bytes of one 4-clip chain (100 steps) from the committed ncu launch list of the DDIM steps
+        ddim_traffic = json.load(open(os.path.join(ROOT, "profiles", "ddim_traffic.json"))).get("dram_bytes_per_chain")
+    except Exception:
+        pass
     out = {"metric": DDIM_METRIC, "value": value, "unit": DDIM_UNIT, "n_gpus": n_gpus, "steps": chains, "warmup": 1,
            "ms_per_step": ms_chain, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic", "config": ddim_config(n_gpus),
@@ -341,7 +346,8 @@ def measure_ddim(dev, rank, n_gpus, chains, peaks, want_cpu, keep=None):
                         "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (a kernel timed inside a long step)"
                                         if peaks else "fallback 1.59 PFLOP/s dense bf16/fp16"),
                         "note": "achieved = 18.66 algorithmic TFLOP per clip x clips per GPU / chain time (all kernels of the "
-                                "chain, not only the GEMMs); traffic: see profiles/", "traffic": None}}
+                                "chain, not only the GEMMs); traffic = DRAM bytes of one chain (profiles/ddim_traffic.json)",
+                        "traffic": ddim_traffic}}
     if want_cpu:
         r, sps, cores = cpu_ddim_rate(3)
         out["cpu_baseline"] = {"value": r, "unit": DDIM_UNIT, "cores": cores, "kind": "port",
