@@ -478,10 +478,13 @@ def run_ours(args):
         step_device()
     if gather is not None:
         gather.drain()
-    barrier()
+    # the clock sampler forks nvidia-smi (tens of ms for a process of this size): start it BEFORE the barrier that aligns
+    # the ranks -- started after it, rank 0 entered the timed loop late and every other rank's time (max over ranks)
+    # included the wait for it at the final gather barrier (0.5 ms per step at N = 2, 6 ms at N = 4 with 10 steps)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    barrier()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
