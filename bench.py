@@ -454,7 +454,9 @@ def run_ours(args):
     # compute grid); AGPT_GATHER=nccl selects the asynchronous NCCL all-gather instead
     gather, gather_kind = None, None
     if n_gpus > 1:
-        if os.environ.get("AGPT_GATHER", "p2p") == "p2p":
+        if os.environ.get("AGPT_GATHER", "p2p") == "none":      # diagnostic: compute-only scaling (no waveform gather)
+            gather, gather_kind = None, "none (diagnostic)"
+        elif os.environ.get("AGPT_GATHER", "p2p") == "p2p":
             try:
                 gather, gather_kind = parallel.P2PGather((B_PER_GPU, 1, T_FRAMES * HOP), device=dev), "p2p_copy_engine"
             except RuntimeError as e:        # raised on every rank together (peer mapping unavailable): NCCL path instead
@@ -496,10 +498,12 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - l0
+    per_rank_ms = None
     if n_gpus > 1:
-        tmax = torch.tensor([ms], device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax.item())
+        allms = [torch.zeros(1, device=dev) for _ in range(n_gpus)]
+        dist.all_gather(allms, torch.tensor([ms], device=dev))
+        per_rank_ms = [float(t.item()) / args.steps for t in allms]
+        ms = max(per_rank_ms) * args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = frames_step / (ms_per_step * 1e-3)
@@ -628,7 +632,7 @@ def run_ours(args):
             "tflops_fp32": 0.614e9 * value / 1e12,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "ddim": ddim, "mixed_dispatch": mixed, "extra": extra,
-            "waveform_gather": gather_kind}
+            "waveform_gather": gather_kind, "ms_per_step_by_rank": per_rank_ms}
     print(json.dumps(line))
     sys.stdout.flush()
     finish()
