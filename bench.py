@@ -450,13 +450,15 @@ def run_ours(args):
     mel_host = specs.synth_tensor((B_PER_GPU, 80, T_FRAMES), seed=100 + rank, scale=2.0, shift=-4.0)
     mel = mel_host.to(dev)
     frames_step = B_PER_GPU * T_FRAMES * n_gpus
-    # finished waveforms -> every rank: copy engines over NVLink (parallel.P2PGather, no SM kernel under the persistent
-    # compute grid); AGPT_GATHER=nccl selects the asynchronous NCCL all-gather instead
+    # finished waveforms -> every rank: asynchronous NCCL all-gather on NCCL's stream under the next step (default), or
+    # AGPT_GATHER=p2p: copy engines over NVLink (parallel.P2PGather).  Measured on one 4-GPU box (profiles/r2w_*): no gather
+    # 18.94 ms per step, NCCL 19.07, copy engines 19.86 -- N - 1 serial peer copies per rank stop paying past N = 2
     gather, gather_kind = None, None
     if n_gpus > 1:
-        if os.environ.get("AGPT_GATHER", "p2p") == "none":      # diagnostic: compute-only scaling (no waveform gather)
+        gsel = os.environ.get("AGPT_GATHER", "nccl")
+        if gsel == "none":      # diagnostic: compute-only scaling (no waveform gather)
             gather, gather_kind = None, "none (diagnostic)"
-        elif os.environ.get("AGPT_GATHER", "p2p") == "p2p":
+        elif gsel == "p2p":
             try:
                 gather, gather_kind = parallel.P2PGather((B_PER_GPU, 1, T_FRAMES * HOP), device=dev), "p2p_copy_engine"
             except RuntimeError as e:        # raised on every rank together (peer mapping unavailable): NCCL path instead
