@@ -151,7 +151,7 @@ struct Unet : Handle {
   static bool planes_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("AGPT_UNET_PLANES"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v == 1 && tc_enabled() && tc_get_version() >= 6;
+    return v == 1 && tc_enabled() && tc_get_version() >= 6 && attention_tc_enabled();   // the plane path's attention writes planes: tcgen05 kernels only
   }
   // out [rows][Cout] = planes [rows][Cin] x W (+ bias, + residual); optionally also planes of the result
   bool linear_planes(const PackedConv& pc, Planes in, int in_pitch, float* out, int out_pitch, long rows, int epi,
