@@ -285,3 +285,31 @@ def test_bigvgan_state_dict_layouts_and_abi_order():
         assert torch.allclose(a, b, atol=1e-7)
     with pytest.raises(RuntimeError, match="CUDA only"):
         m(torch.zeros(1, 80, 4))
+
+
+# ---- bench.py contract of the reference arm (CPU only: it is the one arm that must run without a GPU)
+def test_bench_reference_arm_contract():
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env.pop("RANK", None)
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1                                   # ONE JSON line
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "mel_frames_per_s_vocoded" and d["unit"] == "frames/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["cores"] >= 1 and "mallopt" in cb["sample"]
+    assert abs(d["ms_per_step"] * 1e-3 * d["value"] - d["frames_per_step"]) < 1e-3 * d["frames_per_step"]   # nothing extrapolated
+    assert d["ddim"]["metric"] == "clips_per_s_ddim100_cfg" and d["ddim"]["value"] > 0
+    # every other rank of a torchrun launch exits 0 without work and without output
+    env["RANK"] = "1"
+    r1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                        capture_output=True, text=True, timeout=120, env=env, cwd=root)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
